@@ -1,0 +1,483 @@
+// C-ABI layer (include/b200_whisper.h) and the native engine that sequences the encoder / decoder
+// layer loops (reference: mlx_whisper/whisper.py::AudioEncoder.__call__, TextDecoder.__call__;
+// SURVEY.md A.2; call site /root/reference/run:3-6).
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "b200_whisper.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200w {
+
+// ------------------------------------------------------------------------------------------------ plumbing
+static thread_local char g_err[1024] = "";
+unsigned long long g_launch_count = 0;
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_err; }
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return kErrDriver;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (CUresult %d): base %p rank %d dims [%llu,%llu,%llu] strides [%llu,%llu] box [%u,%u,%u]",
+                   (int)r, base, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                   (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides_bytes[0] : 0),
+                   (unsigned long long)(rank > 2 ? strides_bytes[1] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+    return kErrDriver;
+  }
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM helpers
+// C(M, ldc) = epilogue(A(M, K; lda) W(N, K)^T)
+static int gemm(const void* A, long long lda, int M, const void* W, int N, int K, void* C, long long ldc, bool out_f32,
+                const float* bias, bool gelu, const float* resid, long long resid_ld, int resid_mod,
+                cudaStream_t stream) {
+  B200W_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  B200W_CHECK_ARG((lda * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                  "gemm: operands must be 16-byte aligned");
+  GemmParams p{};
+  p.n_batch = 1;
+  p.rows_per_batch = M;
+  p.N = N;
+  p.K = K;
+  p.n_store = N;
+  p.out = C;
+  p.ldc = ldc;
+  p.out_f32 = out_f32 ? 1 : 0;
+  p.bias = bias;
+  p.resid = resid;
+  p.resid_ld = resid_ld;
+  p.resid_mod = resid_mod;
+  p.gelu = gelu ? 1 : 0;
+  const int bn = gemm_block_n(1, M, N);
+  CUtensorMap ta, tb;
+  B200W_TRY(make_tmap_a(&ta, A, 1, M, K, lda, (long long)M * lda));
+  B200W_TRY(make_tmap_w(&tb, W, N, K, bn));
+  return launch_gemm(ta, tb, p, bn, stream);
+}
+
+static int conv1d_gelu(const void* x_padded, const void* w, const float* bias, int n_batch, int t_in, int c_in,
+                       int c_out, int stride, const float* pos, void* out, long long out_ld, bool out_f32,
+                       cudaStream_t stream) {
+  B200W_CHECK_ARG(stride == 1 || stride == 2, "conv1d: stride must be 1 or 2");
+  B200W_CHECK_ARG(t_in % stride == 0 && c_in % 8 == 0 && c_out % 32 == 0, "conv1d: bad sizes");
+  const int t_out = t_in / stride;
+  GemmParams p{};
+  p.n_batch = n_batch;
+  p.rows_per_batch = t_out;
+  p.N = c_out;
+  p.K = 3 * c_in;
+  p.n_store = c_out;
+  p.out = out;
+  p.ldc = out_ld;
+  p.out_f32 = out_f32 ? 1 : 0;
+  p.bias = bias;
+  p.resid = pos;
+  p.resid_ld = c_out;
+  p.resid_mod = pos ? t_out : 0;
+  p.gelu = 1;
+  const int bn = gemm_block_n(n_batch, t_out, c_out);
+  CUtensorMap ta, tb;
+  // im2col by tensor map: row t of slab b starts at padded row stride*t and spans 3*c_in contiguous values
+  B200W_TRY(make_tmap_a(&ta, x_padded, n_batch, t_out, 3 * c_in, (long long)stride * c_in, (long long)(t_in + 2) * c_in));
+  B200W_TRY(make_tmap_w(&tb, w, c_out, 3 * c_in, bn));
+  return launch_gemm(ta, tb, p, bn, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct Model {
+  b200w_weights w;
+  std::vector<b200w_enc_layer> enc;
+  std::vector<b200w_dec_layer> dec;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carver {
+  unsigned char* base;
+  size_t off = 0, cap;
+  Carver(void* b, size_t c) : base(static_cast<unsigned char*>(b)), cap(c) {}
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off = align_up(off + bytes, 1024);
+    return p;
+  }
+};
+
+struct EncBufs {
+  void *h1, *x, *h, *qkv, *att, *mlp;
+};
+static size_t carve_encoder(const b200w_dims& dm, int B, Carver& c, EncBufs* o) {
+  const size_t d = dm.n_audio_state, T = dm.n_audio_ctx;
+  const size_t rows = (size_t)B * T;
+  // conv1 output, padded NLC slab (B, 2T + 2, d) bf16
+  void* h1 = c.take((size_t)B * (2 * T + 2) * d * 2);
+  void* x = c.take(rows * d * 4);
+  void* h = c.take(rows * d * 2);
+  void* qkv = c.take(rows * 3 * d * 2);
+  void* att = c.take(rows * d * 2);
+  void* mlp = c.take(rows * 4 * d * 2);
+  if (o) *o = EncBufs{h1, x, h, qkv, att, mlp};
+  return c.off;
+}
+
+struct DecBufs {
+  void *x, *h, *qkv, *att, *qc, *mlp;
+};
+static size_t carve_decoder(const b200w_dims& dm, int n_seq, int n_q, Carver& c, DecBufs* o) {
+  const size_t d = dm.n_text_state;
+  const size_t rows = align_up((size_t)n_seq * n_q, 128);  // TMA boxes may read (zero-filled) past M, never past the buffer
+  void* x = c.take(rows * d * 4);
+  void* h = c.take(rows * d * 2);
+  void* qkv = c.take(rows * 3 * d * 2);
+  void* att = c.take(rows * d * 2);
+  void* qc = c.take(rows * d * 2);
+  void* mlp = c.take(rows * 4 * d * 2);
+  if (o) *o = DecBufs{x, h, qkv, att, qc, mlp};
+  return c.off;
+}
+
+}  // namespace b200w
+
+using namespace b200w;
+
+struct b200w_model {
+  Model m;
+};
+
+extern "C" {
+
+const char* b200w_version(void) { return "b200-whisper 0.1 (abi 1, sm_100a)"; }
+const char* b200w_last_error(void) { return get_last_error(); }
+unsigned long long b200w_launch_count(void) { return g_launch_count; }
+
+int b200w_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
+                 int n_mels, const b200w_logmel_tables* t, float* out_unclamped, float* gmax, void* stream) {
+  B200W_CHECK_ARG(pcm && t && out_unclamped && gmax, "logmel: null pointer");
+  return launch_logmel(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, t->hann, t->tw400, t->mel_lo, t->mel_cnt,
+                       t->mel_off, t->mel_w, out_unclamped, gmax, (cudaStream_t)stream);
+}
+
+int b200w_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, void* stream) {
+  B200W_CHECK_ARG(x && gmax && n_audio > 0 && per_audio > 0, "logmel_finalize: bad arguments");
+  return launch_logmel_finalize(x, gmax, n_audio, per_audio, (cudaStream_t)stream);
+}
+
+int b200w_mel_windows(const float* mel, const float* gmax, const long long* row0, const int* size, const int* gidx,
+                      int n_windows, int n_mels, void* dst_bf16, void* stream) {
+  B200W_CHECK_ARG(mel && row0 && size && (gidx || !gmax) && dst_bf16, "mel_windows: null pointer");
+  return launch_mel_windows(mel, gmax, row0, size, gidx, n_windows, n_mels, (__nv_bfloat16*)dst_bf16,
+                            (cudaStream_t)stream);
+}
+
+int b200w_gemm_bf16(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias,
+                    const float* resid, int M, int N, int K, int flags, void* stream) {
+  B200W_CHECK_ARG(A && W && C, "gemm: null pointer");
+  return gemm(A, lda, M, W, N, K, C, ldc, (flags & B200W_GEMM_OUT_F32) != 0, bias, (flags & B200W_GEMM_GELU) != 0, resid,
+              ldc, 0, (cudaStream_t)stream);
+}
+
+int b200w_conv1d_gelu(const void* x_padded, const void* w, const float* bias, int n_batch, int t_in, int c_in,
+                      int c_out, int stride, const float* pos, void* out, long long out_ld, int out_f32, void* stream) {
+  B200W_CHECK_ARG(x_padded && w && out, "conv1d: null pointer");
+  return conv1d_gelu(x_padded, w, bias, n_batch, t_in, c_in, c_out, stride, pos, out, out_ld, out_f32 != 0,
+                     (cudaStream_t)stream);
+}
+
+int b200w_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, void* out_bf16,
+                    float* out_f32, void* stream) {
+  B200W_CHECK_ARG(x && gamma && beta && (out_bf16 || out_f32), "layernorm: null pointer");
+  return launch_layernorm(x, gamma, beta, rows, d, (__nv_bfloat16*)out_bf16, out_f32, (cudaStream_t)stream);
+}
+
+int b200w_encoder_attention(const void* qkv, int n_batch, int T, int n_head, void* out, void* stream) {
+  B200W_CHECK_ARG(qkv && out, "encoder_attention: null pointer");
+  return launch_encoder_attention((const __nv_bfloat16*)qkv, n_batch, T, n_head, (__nv_bfloat16*)out,
+                                  (cudaStream_t)stream);
+}
+
+int b200w_decoder_self_attention(const void* qkv, int n_seq, int n_q, int n_head, const int* pos, void* k_pages,
+                                 void* v_pages, const int* block_table, int max_pages, int page_size, void* out,
+                                 void* stream) {
+  B200W_CHECK_ARG(qkv && pos && k_pages && v_pages && block_table && out, "self_attention: null pointer");
+  return launch_decoder_self_attention((const __nv_bfloat16*)qkv, n_seq, n_q, n_head, pos, (__nv_bfloat16*)k_pages,
+                                       (__nv_bfloat16*)v_pages, block_table, max_pages, page_size, (__nv_bfloat16*)out,
+                                       (cudaStream_t)stream);
+}
+
+int b200w_decoder_cross_attention(const void* q, int n_seq, int n_q, int n_head, const void* cross_kv,
+                                  long long seq_stride, int T, const int* slot, void* out, void* stream) {
+  B200W_CHECK_ARG(q && cross_kv && slot && out, "cross_attention: null pointer");
+  return launch_decoder_cross_attention((const __nv_bfloat16*)q, n_seq, n_q, n_head, (const __nv_bfloat16*)cross_kv,
+                                        seq_stride, T, slot, (__nv_bfloat16*)out, (cudaStream_t)stream);
+}
+
+int b200w_embed(const int* tokens, int tokens_ld, const int* pos, int n_seq, int n_q, const void* tok_emb,
+                const void* pos_emb, int d, int n_ctx, float* x, void* stream) {
+  B200W_CHECK_ARG(tokens && pos && tok_emb && pos_emb && x, "embed: null pointer");
+  return launch_embed(tokens, tokens_ld, pos, n_seq, n_q, (const __nv_bfloat16*)tok_emb, (const __nv_bfloat16*)pos_emb, d,
+                      n_ctx, x, (cudaStream_t)stream);
+}
+
+int b200w_filter_argmax(const float* logits, const uint32_t* suppress_bits, int* tokens, int* n_tokens, int* pos,
+                        float* sum_logprob, int* finished, int n_seq, const b200w_filter_params* fp, void* stream) {
+  B200W_CHECK_ARG(logits && suppress_bits && tokens && n_tokens && pos && sum_logprob && finished && fp,
+                  "filter_argmax: null pointer");
+  return launch_filter_argmax(logits, suppress_bits, tokens, n_tokens, pos, sum_logprob, finished, n_seq, *fp,
+                              (cudaStream_t)stream);
+}
+
+int b200w_no_speech_prob(const float* logits, int logits_ld, int n_seq, int n_vocab, int no_speech, float* out,
+                         void* stream) {
+  B200W_CHECK_ARG(logits && out && n_seq > 0, "no_speech_prob: bad arguments");
+  return launch_no_speech(logits, logits_ld, n_seq, n_vocab, no_speech, out, (cudaStream_t)stream);
+}
+
+int b200w_detect_language(const float* logits, int logits_ld, int n_seq, int lang_begin, int n_lang, int* lang_token,
+                          float* lang_probs, void* stream) {
+  B200W_CHECK_ARG(logits && lang_token && lang_probs && n_seq > 0 && n_lang > 0, "detect_language: bad arguments");
+  return launch_language(logits, logits_ld, n_seq, lang_begin, n_lang, lang_token, lang_probs, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------- engine
+int b200w_model_create(const b200w_weights* w, b200w_model** out) {
+  B200W_CHECK_ARG(w && out && w->h_enc_layers && w->h_dec_layers, "model_create: null pointer");
+  const b200w_dims& dm = w->dims;
+  B200W_CHECK_ARG(dm.n_audio_state == dm.n_audio_head * 64 && dm.n_text_state == dm.n_text_head * 64,
+                  "model_create: head dim must be 64");
+  B200W_CHECK_ARG(dm.n_audio_state % 128 == 0 && dm.n_text_state % 128 == 0 && dm.n_audio_state <= 1280 &&
+                      dm.n_text_state <= 1280,
+                  "model_create: widths must be multiples of 128 up to 1280");
+  B200W_CHECK_ARG(dm.n_audio_ctx == 1500 && dm.n_text_ctx <= 448, "model_create: unsupported context sizes");
+  B200W_TRY(init_gemm());
+  B200W_TRY(init_attention());
+  B200W_TRY(init_logmel());
+  b200w_model* m = new (std::nothrow) b200w_model();
+  B200W_CHECK_ARG(m != nullptr, "model_create: out of host memory");
+  m->m.w = *w;
+  m->m.enc.assign(w->h_enc_layers, w->h_enc_layers + dm.n_audio_layer);
+  m->m.dec.assign(w->h_dec_layers, w->h_dec_layers + dm.n_text_layer);
+  m->m.w.h_enc_layers = m->m.enc.data();
+  m->m.w.h_dec_layers = m->m.dec.data();
+  *out = m;
+  return kOk;
+}
+
+void b200w_model_destroy(b200w_model* m) { delete m; }
+
+size_t b200w_encoder_workspace_bytes(const b200w_model* m, int n_windows) {
+  if (!m || n_windows <= 0) return 0;
+  Carver c(nullptr, 0);
+  return carve_encoder(m->m.w.dims, n_windows, c, nullptr);
+}
+
+int b200w_encoder_forward(const b200w_model* mp, const void* mel_padded, int B, void* workspace, size_t workspace_bytes,
+                          void* xa_bf16, float* xa_f32, int stop_after_layers, void* stream_) {
+  B200W_CHECK_ARG(mp && mel_padded && workspace && B > 0, "encoder_forward: bad arguments");
+  const Model& m = mp->m;
+  const b200w_dims& dm = m.w.dims;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int d = dm.n_audio_state, T = dm.n_audio_ctx, H = dm.n_audio_head;
+  const int rows = B * T;
+  Carver c(workspace, workspace_bytes);
+  EncBufs bf;
+  if (carve_encoder(dm, B, c, &bf) > workspace_bytes) {
+    set_last_error("encoder_forward: workspace too small (%zu < %zu)", workspace_bytes, c.off);
+    return kErrWorkspace;
+  }
+  // conv1 (+GELU) -> rows 1..2T of each (2T + 2, d) padded slab; rows 0 and 2T+1 stay zero (conv2's padding)
+  B200W_CUDA_OK(cudaMemsetAsync(bf.h1, 0, (size_t)B * (2 * T + 2) * d * 2, stream));
+  {
+    GemmParams p{};
+    p.n_batch = B;
+    p.rows_per_batch = 2 * T;
+    p.out_batch_rows = 2 * T + 2;
+    p.N = d;
+    p.K = 3 * dm.n_mels;
+    p.n_store = d;
+    p.out = static_cast<unsigned char*>(bf.h1) + (size_t)d * 2;  // skip the leading pad row
+    p.ldc = d;
+    p.out_f32 = 0;
+    p.bias = m.w.conv1_b;
+    p.gelu = 1;
+    const int bn = gemm_block_n(B, 2 * T, d);
+    CUtensorMap ta, tb;
+    B200W_TRY(make_tmap_a(&ta, mel_padded, B, 2 * T, 3 * dm.n_mels, dm.n_mels, (long long)(2 * T + 2) * dm.n_mels));
+    B200W_TRY(make_tmap_w(&tb, m.w.conv1_w, d, 3 * dm.n_mels, bn));
+    B200W_TRY(launch_gemm(ta, tb, p, bn, stream));
+  }
+  // conv2 (stride 2) + GELU + sinusoidal positions -> f32 residual stream
+  B200W_TRY(conv1d_gelu(bf.h1, m.w.conv2_w, m.w.conv2_b, B, 2 * T, d, d, 2, m.w.enc_pos, bf.x, d, true, stream));
+
+  float* x = static_cast<float*>(bf.x);
+  const int n_layers = (stop_after_layers >= 0 && stop_after_layers < dm.n_audio_layer) ? stop_after_layers
+                                                                                         : dm.n_audio_layer;
+  for (int l = 0; l < n_layers; ++l) {
+    const b200w_enc_layer& L = m.enc[l];
+    B200W_TRY(launch_layernorm(x, L.attn_ln_g, L.attn_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.qkv, 3 * d, false, L.b_qkv, false, nullptr, 0, 0, stream));
+    B200W_TRY(launch_encoder_attention((const __nv_bfloat16*)bf.qkv, B, T, H, (__nv_bfloat16*)bf.att, stream));
+    B200W_TRY(gemm(bf.att, d, rows, L.w_out, d, d, x, d, true, L.b_out, false, x, d, 0, stream));
+    B200W_TRY(launch_layernorm(x, L.mlp_ln_g, L.mlp_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));
+    B200W_TRY(gemm(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, x, d, true, L.b_mlp2, false, x, d, 0, stream));
+  }
+  if (stop_after_layers >= 0) {
+    B200W_CHECK_ARG(xa_f32 != nullptr, "encoder_forward: probe mode needs xa_f32");
+    B200W_CUDA_OK(cudaMemcpyAsync(xa_f32, x, (size_t)rows * d * 4, cudaMemcpyDeviceToDevice, stream));
+    return kOk;
+  }
+  B200W_CHECK_ARG(xa_bf16 || xa_f32, "encoder_forward: no output buffer");
+  return launch_layernorm(x, m.w.ln_post_g, m.w.ln_post_b, rows, d, (__nv_bfloat16*)xa_bf16, xa_f32, stream);
+}
+
+int b200w_cross_kv(const b200w_model* mp, const void* xa_bf16, int B, void* cross_kv, long long layer_stride, int slot0,
+                   void* stream_) {
+  B200W_CHECK_ARG(mp && xa_bf16 && cross_kv && B > 0 && slot0 >= 0, "cross_kv: bad arguments");
+  const Model& m = mp->m;
+  const b200w_dims& dm = m.w.dims;
+  const int d = dm.n_text_state, T = dm.n_audio_ctx;
+  B200W_CHECK_ARG(dm.n_audio_state == d, "cross_kv: encoder/decoder widths differ");
+  for (int l = 0; l < dm.n_text_layer; ++l) {
+    const b200w_dec_layer& L = m.dec[l];
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(cross_kv) + (size_t)l * layer_stride + (size_t)slot0 * T * 2 * d;
+    B200W_TRY(gemm(xa_bf16, d, B * T, L.w_ckv, 2 * d, d, dst, 2 * d, false, L.b_ckv, false, nullptr, 0, 0,
+                   (cudaStream_t)stream_));
+  }
+  return kOk;
+}
+
+size_t b200w_decoder_workspace_bytes(const b200w_model* m, int n_seq, int n_q) {
+  if (!m || n_seq <= 0 || n_q <= 0) return 0;
+  Carver c(nullptr, 0);
+  return carve_decoder(m->m.w.dims, n_seq, n_q, c, nullptr);
+}
+
+int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int n_q, int sot_index, int select,
+                       const b200w_filter_params* fp, void* workspace, size_t workspace_bytes, void* stream_) {
+  B200W_CHECK_ARG(mp && st && workspace && n_q > 0, "decoder_step: bad arguments");
+  B200W_CHECK_ARG(!select || fp, "decoder_step: select needs filter params");
+  const Model& m = mp->m;
+  const b200w_dims& dm = m.w.dims;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int d = dm.n_text_state, H = dm.n_text_head, T = dm.n_audio_ctx, B = st->n_seq;
+  const int rows = B * n_q;
+  B200W_CHECK_ARG(B > 0 && sot_index < n_q, "decoder_step: bad n_seq / sot_index");
+  B200W_CHECK_ARG(st->logits_ld >= ((dm.n_vocab + 127) / 128) * 128, "decoder_step: logits_ld too small");
+  Carver c(workspace, workspace_bytes);
+  DecBufs bf;
+  if (carve_decoder(dm, B, n_q, c, &bf) > workspace_bytes) {
+    set_last_error("decoder_step: workspace too small (%zu < %zu)", workspace_bytes, c.off);
+    return kErrWorkspace;
+  }
+  float* x = static_cast<float*>(bf.x);
+  B200W_TRY(launch_embed(st->tokens, st->tokens_ld, st->pos, B, n_q, (const __nv_bfloat16*)m.w.tok_emb,
+                         (const __nv_bfloat16*)m.w.dec_pos, d, dm.n_text_ctx, x, stream));
+  for (int l = 0; l < dm.n_text_layer; ++l) {
+    const b200w_dec_layer& L = m.dec[l];
+    __nv_bfloat16* kp = static_cast<__nv_bfloat16*>(st->k_pages) + (size_t)l * st->layer_page_stride;
+    __nv_bfloat16* vp = static_cast<__nv_bfloat16*>(st->v_pages) + (size_t)l * st->layer_page_stride;
+    const __nv_bfloat16* ckv = static_cast<const __nv_bfloat16*>(st->cross_kv) + (size_t)l * st->cross_layer_stride;
+    B200W_TRY(launch_layernorm(x, L.attn_ln_g, L.attn_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.qkv, 3 * d, false, L.b_qkv, false, nullptr, 0, 0, stream));
+    B200W_TRY(launch_decoder_self_attention((const __nv_bfloat16*)bf.qkv, B, n_q, H, st->pos, kp, vp, st->block_table,
+                                            st->max_pages, st->page_size, (__nv_bfloat16*)bf.att, stream));
+    B200W_TRY(gemm(bf.att, d, rows, L.w_out, d, d, x, d, true, L.b_out, false, x, d, 0, stream));
+    B200W_TRY(launch_layernorm(x, L.cross_ln_g, L.cross_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_cq, d, d, bf.qc, d, false, L.b_cq, false, nullptr, 0, 0, stream));
+    B200W_TRY(launch_decoder_cross_attention((const __nv_bfloat16*)bf.qc, B, n_q, H, ckv, (long long)T * 2 * d, T,
+                                             st->cross_slot, (__nv_bfloat16*)bf.att, stream));
+    B200W_TRY(gemm(bf.att, d, rows, L.w_cout, d, d, x, d, true, L.b_cout, false, x, d, 0, stream));
+    B200W_TRY(launch_layernorm(x, L.mlp_ln_g, L.mlp_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));
+    B200W_TRY(gemm(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, x, d, true, L.b_mlp2, false, x, d, 0, stream));
+  }
+  B200W_TRY(launch_layernorm(x, m.w.dec_ln_g, m.w.dec_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+  // tied logits, last new token of every sequence: a strided view of h (row stride n_q * d)
+  const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(bf.h);
+  {
+    GemmParams p{};
+    p.n_batch = 1;
+    p.rows_per_batch = B;
+    p.N = dm.n_vocab;
+    p.K = d;
+    p.n_store = dm.n_vocab;
+    p.ldc = st->logits_ld;
+    p.out_f32 = 1;
+    const int bn = 128;
+    CUtensorMap ta, tb;
+    B200W_TRY(make_tmap_w(&tb, m.w.tok_emb, dm.n_vocab, d, bn));
+    p.out = st->logits;
+    B200W_TRY(make_tmap_a(&ta, h + (size_t)(n_q - 1) * d, 1, B, d, (long long)n_q * d, (long long)B * n_q * d));
+    B200W_TRY(launch_gemm(ta, tb, p, bn, stream));
+    if (sot_index >= 0) {
+      B200W_CHECK_ARG(st->logits_aux && st->no_speech && fp, "decoder_step: no_speech buffers missing");
+      p.out = st->logits_aux;
+      B200W_TRY(make_tmap_a(&ta, h + (size_t)sot_index * d, 1, B, d, (long long)n_q * d, (long long)B * n_q * d));
+      B200W_TRY(launch_gemm(ta, tb, p, bn, stream));
+      B200W_TRY(launch_no_speech(st->logits_aux, st->logits_ld, B, dm.n_vocab, fp->no_speech, st->no_speech, stream));
+    }
+  }
+  if (select) {
+    B200W_TRY(launch_filter_argmax(st->logits, st->suppress_bits, st->tokens, st->n_tokens, st->pos, st->sum_logprob,
+                                   st->finished, B, *fp, stream));
+  }
+  return kOk;
+}
+
+}  // extern "C"

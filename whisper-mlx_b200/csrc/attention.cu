@@ -1,0 +1,497 @@
+// K6 / K7 / K8: attention kernels (reference: mlx_whisper/whisper.py::MultiHeadAttention.qkv_attention,
+// reached from /root/reference/run:3-6).  Head dim is 64 for every Whisper size; the
+// reference scales q and k by hd^-0.25 each, here the product hd^-0.5 is folded into the fp32 scores.
+//
+// K6 encoder MHA (non-causal, S = 1500): flash-style on tcgen05.  One CTA = 128 queries of one head.
+//    Q/K/V tiles arrive by TMA (128-byte swizzle) straight out of the fused QKV activation;
+//    S = Q K^T (128x128x64) and O_blk = P V (128x64x128, V consumed MN-major) run on the tensor cores
+//    with accumulators in TMEM; each of the 128 threads owns one query row (one TMEM lane): softmax
+//    needs no shuffles, P goes back to shared memory as the swizzled bf16 A operand, and the running
+//    output is rescaled in registers.  Two CTAs per SM overlap one CTA's exp work with the other's MMAs.
+// K7 decoder self-attention over the paged KV cache (q-len 1, or a short prompt), CUDA cores.
+// K8 decoder cross-attention (S = 1500), the HBM-bound hot spot of decoding: 16-byte coalesced loads,
+//    8 lanes per key row, each K/V byte read exactly once per step.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200w {
+
+constexpr int kHd = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// descriptor for an MN-major or K-major SW128 tile with explicit leading byte offset
+__device__ __forceinline__ uint64_t make_sw128_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// =============================================================================================== K6
+constexpr int kEncThreads = 128;
+constexpr int kBQ = 128;
+constexpr int kBKV = 128;
+constexpr int kTileBytes = 128 * kHd * 2;  // 16 KB: 128 rows x 128 B
+constexpr int kEncSmem = 3 * kTileBytes + 2 * kTileBytes + 1024 + 128;
+
+__global__ void __launch_bounds__(kEncThreads, 2)
+encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, int T, int d, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ unsigned char att_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sK = smem + kTileBytes;
+  unsigned char* sV = smem + 2 * kTileBytes;
+  unsigned char* sP = smem + 3 * kTileBytes;  // two 16 KB K-major sub-tiles (keys 0-63, 64-127)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_o = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
+  const int nkv = (T + kBKV - 1) / kBKV;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_o = tmem_s + 128;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, kTileBytes);
+    tma_load_3d(sQ, &tm_qkv, bar_q, h * kHd, q0, b);
+    mbar_expect_tx(bar_k, kTileBytes);
+    tma_load_3d(sK, &tm_qkv, bar_k, d + h * kHd, 0, b);
+    mbar_expect_tx(bar_v, kTileBytes);
+    tma_load_3d(sV, &tm_qkv, bar_v, 2 * d + h * kHd, 0, b);
+  }
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
+  const float c = 0.125f * kLog2e;                              // hd^-0.5 in the exp2 domain
+
+  float m_run = -INFINITY, l_run = 0.0f;
+  float o[kHd];
+#pragma unroll
+  for (int i = 0; i < kHd; ++i) o[i] = 0.0f;
+  const int row = tid;  // query row within the tile == TMEM lane
+
+  for (int j = 0; j < nkv; ++j) {
+    const uint32_t ph = j & 1;
+    if (tid == 0) {
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, ph);
+      tcgen05_fence_after();
+      const uint64_t qd = make_sw128_desc(smem_u32(sQ));
+      const uint64_t kd = make_sw128_desc(smem_u32(sK));
+#pragma unroll
+      for (int k = 0; k < kHd / 16; ++k) umma_f16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    mbar_wait(bar_s, ph);
+    tcgen05_fence_after();
+    if (tid == 0 && j + 1 < nkv) {  // K tile is free again
+      mbar_expect_tx(bar_k, kTileBytes);
+      tma_load_3d(sK, &tm_qkv, bar_k, d + h * kHd, (j + 1) * kBKV, b);
+    }
+    __syncwarp();
+
+    const int kv_valid = min(kBKV, T - j * kBKV);
+    // pass 1: row maximum
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_s + cb * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float s = (cb * 32 + i < kv_valid) ? __uint_as_float(r[i]) : -INFINITY;
+        mx = fmaxf(mx, s);
+      }
+    }
+    const float m_new = fmaxf(m_run, mx * c);
+    const float alpha = fast_exp2(m_run - m_new);
+    m_run = m_new;
+    // pass 2: probabilities -> swizzled bf16 A operand
+    float psum = 0.0f;
+#pragma unroll 1
+    for (int cb = 0; cb < 4; ++cb) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_s + cb * 32, r);
+      tmem_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c0 = cb * 32 + 2 * i;
+        float p0 = (c0 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(r[2 * i]), c, -m_new)) : 0.0f;
+        float p1 = (c0 + 1 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new)) : 0.0f;
+        psum += p0 + p1;
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+      // columns cb*32 .. +31 -> sub-tile cb/2, 16-byte pieces (cb%2)*4 .. +3, XOR-swizzled with row%8
+      unsigned char* base = sP + (cb >> 1) * kTileBytes + row * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int piece = ((cb & 1) * 4 + q) ^ (row & 7);
+        *reinterpret_cast<uint4*>(base + piece * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+    }
+    l_run = l_run * alpha + psum;
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_fence_after();
+      mbar_wait(bar_v, ph);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int k = 0; k < kBKV / 16; ++k) {
+        const uint64_t pd = make_sw128_desc(smem_u32(sP + (k >> 2) * kTileBytes)) + 2 * (k & 3);
+        const uint64_t vd = make_sw128_desc_lbo(smem_u32(sV + k * 2048), kBKV * 128);
+        umma_f16(tmem_base + 128, pd, vd, idesc_o, k != 0);
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+    mbar_wait(bar_o, ph);
+    tcgen05_fence_after();
+    if (tid == 0 && j + 1 < nkv) {  // V tile (and P) are free again
+      mbar_expect_tx(bar_v, kTileBytes);
+      tma_load_3d(sV, &tm_qkv, bar_v, 2 * d + h * kHd, (j + 1) * kBKV, b);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_o + cb * 32, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[cb * 32 + i] = fmaf(o[cb * 32 + i], alpha, __uint_as_float(r[i]));
+    }
+    tcgen05_fence_before();
+  }
+
+  if (q0 + row < T) {
+    const float inv = 1.0f / l_run;
+    uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * T + q0 + row) * d + h * kHd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dst[i] = make_uint4(pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
+                          pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv), pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int init_attention() {
+  static bool done = false;
+  if (done) return kOk;
+  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmem));
+  done = true;
+  return kOk;
+}
+
+int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n_head, __nv_bfloat16* out,
+                             cudaStream_t stream) {
+  B200W_CHECK_ARG(n_batch > 0 && n_batch <= 65535 && T > 0 && n_head > 0, "encoder_attention: bad sizes");
+  const int d = n_head * kHd;
+  CUtensorMap tm;
+  uint64_t dims[3] = {(uint64_t)(3 * d), (uint64_t)T, (uint64_t)n_batch};
+  uint64_t strides[2] = {(uint64_t)(3 * d) * 2, (uint64_t)T * 3 * d * 2};
+  uint32_t box[3] = {kHd, 128, 1};
+  B200W_TRY(encode_tmap_bf16(&tm, qkv, 3, dims, strides, box));
+  B200W_TRY(init_attention());
+  dim3 grid(ceil_div(T, kBQ), n_head, n_batch);
+  encoder_attention_kernel<<<grid, kEncThreads, kEncSmem, stream>>>(tm, T, d, out);
+  B200W_LAUNCH_OK();
+  count_launch();
+  return kOk;
+}
+
+// =============================================================================================== K7
+constexpr int kSelfThreads = 128;
+constexpr int kMaxSelfKeys = 448;
+
+__global__ void __launch_bounds__(kSelfThreads)
+decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_q, int n_head, const int* __restrict__ pos,
+                              __nv_bfloat16* __restrict__ k_pages, __nv_bfloat16* __restrict__ v_pages,
+                              const int* __restrict__ block_table, int max_pages, int page_size,
+                              __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_q[kHd];
+  __shared__ float s_p[kMaxSelfKeys];
+  __shared__ float s_red[kSelfThreads / 32];
+  __shared__ float s_acc[2][kHd];
+
+  const int h = blockIdx.x, b = blockIdx.y, qi = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = n_head * kHd;
+  const int p0 = pos[b];             // tokens already cached for this sequence
+  const int n_keys = p0 + qi + 1;    // causal
+  const long long my_row = ((long long)b * n_q + qi) * 3 * d;
+
+  // append this token's k / v rows to the paged cache (each (b, h, qi) block owns its 64-wide slice)
+  if (tid < 16) {
+    const int j = p0 + qi;
+    const int page = block_table[b * max_pages + j / page_size];
+    const long long dst = ((long long)page * page_size + j % page_size) * d + h * kHd;
+    const uint4* ks = reinterpret_cast<const uint4*>(qkv + my_row + d + h * kHd);
+    const uint4* vs = reinterpret_cast<const uint4*>(qkv + my_row + 2 * d + h * kHd);
+    if (tid < 8) reinterpret_cast<uint4*>(k_pages + dst)[tid] = ks[tid];
+    else reinterpret_cast<uint4*>(v_pages + dst)[tid - 8] = vs[tid - 8];
+  }
+  if (tid < kHd) s_q[tid] = __bfloat162float(qkv[my_row + h * kHd + tid]) * (0.125f * kLog2e);
+  __syncthreads();
+
+  // rows of position j: cached pages for j < p0, this step's qkv rows otherwise (other blocks write those)
+  auto k_row = [&](int j) -> const __nv_bfloat16* {
+    if (j >= p0) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + d + h * kHd;
+    const int page = block_table[b * max_pages + j / page_size];
+    return k_pages + ((long long)page * page_size + j % page_size) * d + h * kHd;
+  };
+  auto v_row = [&](int j) -> const __nv_bfloat16* {
+    if (j >= p0) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + 2 * d + h * kHd;
+    const int page = block_table[b * max_pages + j / page_size];
+    return v_pages + ((long long)page * page_size + j % page_size) * d + h * kHd;
+  };
+
+  float mx = -INFINITY;
+  for (int j = tid; j < n_keys; j += kSelfThreads) {
+    const uint4* kr = reinterpret_cast<const uint4*>(k_row(j));
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 u = kr[c];
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      acc = fmaf(a0.x, s_q[8 * c + 0], acc);
+      acc = fmaf(a0.y, s_q[8 * c + 1], acc);
+      acc = fmaf(a1.x, s_q[8 * c + 2], acc);
+      acc = fmaf(a1.y, s_q[8 * c + 3], acc);
+      acc = fmaf(a2.x, s_q[8 * c + 4], acc);
+      acc = fmaf(a2.y, s_q[8 * c + 5], acc);
+      acc = fmaf(a3.x, s_q[8 * c + 6], acc);
+      acc = fmaf(a3.y, s_q[8 * c + 7], acc);
+    }
+    s_p[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  float sum = 0.0f;
+  for (int j = tid; j < n_keys; j += kSelfThreads) {
+    const float p = fast_exp2(s_p[j] - mx);
+    s_p[j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  sum = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+
+  // output: two groups of 64 threads split the keys, thread owns one of the 64 dims
+  const int g = tid >> 6, dim = tid & 63;
+  float acc = 0.0f;
+  for (int j = g; j < n_keys; j += 2) {
+    const float p = __bfloat162float(__float2bfloat16(s_p[j]));  // bf16 probabilities, as in the tensor-core path
+    acc = fmaf(p, __bfloat162float(v_row(j)[dim]), acc);
+  }
+  s_acc[g][dim] = acc;
+  __syncthreads();
+  if (tid < kHd) {
+    const float v = (s_acc[0][tid] + s_acc[1][tid]) / sum;
+    out[((long long)b * n_q + qi) * d + h * kHd + tid] = __float2bfloat16(v);
+  }
+}
+
+int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, int n_head, const int* pos,
+                                  __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, const int* block_table,
+                                  int max_pages_per_seq, int page_size, __nv_bfloat16* out, cudaStream_t stream) {
+  B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "self_attention: bad sizes");
+  B200W_CHECK_ARG(max_pages_per_seq * page_size <= kMaxSelfKeys, "self_attention: context above %d", kMaxSelfKeys);
+  dim3 grid(n_head, n_seq, n_q);
+  decoder_self_attention_kernel<<<grid, kSelfThreads, 0, stream>>>(qkv, n_q, n_head, pos, k_pages, v_pages,
+                                                                   block_table, max_pages_per_seq, page_size, out);
+  B200W_LAUNCH_OK();
+  count_launch();
+  return kOk;
+}
+
+// =============================================================================================== K8
+constexpr int kCrossThreads = 256;
+constexpr int kCrossWarps = kCrossThreads / 32;
+constexpr int kMaxCrossKeys = 1536;
+
+__global__ void __launch_bounds__(kCrossThreads)
+decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int n_head,
+                               const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride, int T,
+                               const int* __restrict__ slot, __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_p[kMaxCrossKeys];
+  __shared__ float s_red[kCrossWarps];
+  __shared__ float s_part[kCrossWarps][kHd];
+
+  const int h = blockIdx.x, b = blockIdx.y, qi = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & 7;   // which 8-wide slice of the head dim
+  const int kg = lane >> 3;   // which of the warp's 4 concurrent keys
+  const int d = n_head * kHd;
+  const long long ld = 2ll * d;  // K | V interleaved per row
+  const __nv_bfloat16* kbase = cross_kv + (long long)slot[b] * seq_stride + h * kHd + sub * 8;
+  const __nv_bfloat16* vbase = kbase + d;
+
+  float qv[8];
+  {
+    const uint4 u = *reinterpret_cast<const uint4*>(q + ((long long)b * n_q + qi) * d + h * kHd + sub * 8);
+    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+    const float c = 0.125f * kLog2e;
+    qv[0] = a0.x * c; qv[1] = a0.y * c; qv[2] = a1.x * c; qv[3] = a1.y * c;
+    qv[4] = a2.x * c; qv[5] = a2.y * c; qv[6] = a3.x * c; qv[7] = a3.y * c;
+  }
+
+  // ---- scores: 4 keys per warp per load instruction, 4 loads in flight per thread ----
+  constexpr int kStep = kCrossWarps * 4;  // keys per CTA sweep
+  float mx = -INFINITY;
+  for (int j0 = warp * 4 + kg; j0 < T; j0 += 4 * kStep) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + i * kStep;
+      u[i] = (j < T) ? __ldg(reinterpret_cast<const uint4*>(kbase + j * ld)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + i * kStep;
+      const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z),
+                   a3 = unpack_bf16x2(u[i].w);
+      float s = a0.x * qv[0];
+      s = fmaf(a0.y, qv[1], s);
+      s = fmaf(a1.x, qv[2], s);
+      s = fmaf(a1.y, qv[3], s);
+      s = fmaf(a2.x, qv[4], s);
+      s = fmaf(a2.y, qv[5], s);
+      s = fmaf(a3.x, qv[6], s);
+      s = fmaf(a3.y, qv[7], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (j < T) {
+        if (sub == 0) s_p[j] = s;
+        mx = fmaxf(mx, s);
+      }
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int i = 1; i < kCrossWarps; ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
+  float sum = 0.0f;
+  for (int j = tid; j < T; j += kCrossThreads) {
+    const float p = fast_exp2(s_p[j] - mx);
+    sum += p;
+    s_p[j] = __bfloat162float(__float2bfloat16(p));  // bf16 probabilities, as in the tensor-core path
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kCrossWarps; ++i) sum += s_red[i];
+
+  // ---- output ----
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int j0 = warp * 4 + kg; j0 < T; j0 += 4 * kStep) {
+    uint4 u[4];
+    float p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + i * kStep;
+      u[i] = (j < T) ? __ldg(reinterpret_cast<const uint4*>(vbase + j * ld)) : make_uint4(0, 0, 0, 0);
+      p[i] = (j < T) ? s_p[j] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z),
+                   a3 = unpack_bf16x2(u[i].w);
+      acc[0] = fmaf(p[i], a0.x, acc[0]);
+      acc[1] = fmaf(p[i], a0.y, acc[1]);
+      acc[2] = fmaf(p[i], a1.x, acc[2]);
+      acc[3] = fmaf(p[i], a1.y, acc[3]);
+      acc[4] = fmaf(p[i], a2.x, acc[4]);
+      acc[5] = fmaf(p[i], a2.y, acc[5]);
+      acc[6] = fmaf(p[i], a3.x, acc[6]);
+      acc[7] = fmaf(p[i], a3.y, acc[7]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (kg == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_part[warp][sub * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < kHd) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kCrossWarps; ++w) v += s_part[w][tid];
+    out[((long long)b * n_q + qi) * d + h * kHd + tid] = __float2bfloat16(v / sum);
+  }
+}
+
+int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, int n_head,
+                                   const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
+                                   __nv_bfloat16* out, cudaStream_t stream) {
+  B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "cross_attention: bad sizes");
+  B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
+  dim3 grid(n_head, n_seq, n_q);
+  decoder_cross_attention_kernel<<<grid, kCrossThreads, 0, stream>>>(q, n_q, n_head, cross_kv, seq_stride, T, slot,
+                                                                     out);
+  B200W_LAUNCH_OK();
+  count_launch();
+  return kOk;
+}
+
+}  // namespace b200w

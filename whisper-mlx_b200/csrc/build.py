@@ -1,0 +1,73 @@
+"""Builds libb200whisper.so (all sm_100a kernels + the C ABI) in-tree with nvcc.
+
+The .so lands next to the sources so that it travels with the repo snapshot to the GPU box; it is
+git-ignored.  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "elementwise.cu", "logmel.cu"]
+HEADERS = ["common.cuh", "kernels.h", "logmel_core.h", os.path.join(REPO, "include", "b200_whisper.h")]
+LIB = os.path.join(HERE, "libb200whisper.so")
+STAMP = os.path.join(HERE, ".build_stamp")
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fPIC", "-shared",
+    "-I" + os.path.join(REPO, "include"), "-I" + HERE,
+    "-cudart", "static",
+]
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS + [os.path.abspath(__file__)]:
+        p = f if os.path.isabs(f) else os.path.join(HERE, f)
+        with open(p, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def nvcc_path() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libb200whisper.so")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    digest = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+        return LIB
+    # compile translation units in parallel, then link
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(HERE, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc_path()] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", os.path.join(HERE, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+    cmd = [nvcc_path(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    subprocess.run(cmd, check=True)
+    with open(STAMP, "w") as f:
+        f.write(digest)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,307 @@
+// K5: bf16 GEMM on the 5th-generation tensor cores.  C[M,N] = epilogue(A[M,K] * W[N,K]^T).
+//
+// Replaces every `nn.Linear` / `nn.Conv1d` / `token_embedding.as_linear` matmul that mlx_whisper's
+// AudioEncoder / TextDecoder issue (reference call site
+// /root/reference/run:3-6).
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0   : TMA producer   - cp.async.bulk.tensor tiles of A (128 x 64) and W (BN x 64), 128-byte swizzle,
+//                               kStages-deep mbarrier ring
+//   warp 1   : MMA issuer     - one lane issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16), fp32
+//                               accumulators live in TMEM, double buffered across tiles
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue       - tcgen05.ld 32x32b -> bias / exact GELU / fp32 residual (or positional table)
+//                               -> bf16 or fp32 row-contiguous 16-byte global stores
+// A is addressed through a 3-D tensor map (k, row-in-batch, batch) so that the conv stem runs as an
+// implicit GEMM: with a (T+2, C) zero-padded NLC slab the im2col row of output t is the contiguous
+// 3*C span starting at padded row stride*t, i.e. just a tensor map with an overlapping row stride.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200w {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ unsigned char gemm_smem_raw[];
+  // 1024-byte alignment for the 128B-swizzle atoms
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty_bar = bars + 2 * Cfg::kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = p.n_batch * p.tiles_m_per_batch;
+  const int num_tiles = tiles_m * p.tiles_n;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile id -> (m tile, n tile): groups of group_m row tiles sweep all n tiles so the A rows of a group
+  // stay L2-resident while W (small) is re-read from L2.
+  auto decode_tile = [&](int id, int& mt, int& nt) {
+    const int per_group = p.group_m * p.tiles_n;
+    const int g = id / per_group;
+    const int first_m = g * p.group_m;
+    const int gsize = min(p.group_m, tiles_m - first_m);
+    const int within = id - g * per_group;
+    nt = within / gsize;
+    mt = first_m + (within - nt * gsize);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int mt, nt;
+        decode_tile(tile, mt, nt);
+        const int b = mt / p.tiles_m_per_batch;
+        const int t0 = (mt - b * p.tiles_m_per_batch) * kBM;
+        const int n0 = nt * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * Cfg::kStageBytes;
+          unsigned char* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_3d(sa, &tma_a, &full_bar[stage], kb * kBK, t0, b);
+          tma_load_3d(sb, &tma_b, &full_bar[stage], kb * kBK, n0, 0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t a_desc = make_sw128_desc(sa);
+          const uint64_t b_desc = make_sw128_desc(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes along the swizzled row per K=16 slice -> +2 in the (addr >> 4) field
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int mt, nt;
+      decode_tile(tile, mt, nt);
+      const int b = mt / p.tiles_m_per_batch;
+      const int t = (mt - b * p.tiles_m_per_batch) * kBM + q * 32 + lane;
+      const bool row_ok = t < p.rows_per_batch;
+      const long long row = (long long)b * p.rows_per_batch + t;   // logical row (residual / positional index)
+      const long long orow = (long long)b * p.out_batch_rows + t;  // storage row
+      const int n0 = nt * BN;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col = n0 + c * 32;
+        if (col >= p.n_store) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(t_base + c * 32, r);
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(bp + j);
+            v[4 * j + 0] += bb.x;
+            v[4 * j + 1] += bb.y;
+            v[4 * j + 2] += bb.z;
+            v[4 * j + 3] += bb.w;
+          }
+        }
+        if (p.gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (row_ok) {
+          if (p.resid != nullptr) {
+            const long long rr = (p.resid_mod > 0) ? (row % p.resid_mod) : row;
+            const float4* rp = reinterpret_cast<const float4*>(p.resid + rr * p.resid_ld + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = rp[j];
+              v[4 * j + 0] += x.x;
+              v[4 * j + 1] += x.y;
+              v[4 * j + 2] += x.z;
+              v[4 * j + 3] += x.w;
+            }
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldc + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// Opt every instantiation into its dynamic shared memory size once, up front (never inside a stream capture).
+int init_gemm() {
+  static bool done = false;
+  if (done) return kOk;
+  B200W_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::kSmemBytes));
+  B200W_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::kSmemBytes));
+  B200W_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::kSmemBytes));
+  B200W_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<32>::kSmemBytes));
+  done = true;
+  return kOk;
+}
+
+template <int BN>
+static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, GemmParams p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  B200W_TRY(init_gemm());
+  if (p.out_batch_rows <= 0) p.out_batch_rows = p.rows_per_batch;
+  p.tiles_m_per_batch = ceil_div(p.rows_per_batch, kBM);
+  p.tiles_n = ceil_div(p.n_store, BN);
+  const long long tiles = (long long)p.n_batch * p.tiles_m_per_batch * p.tiles_n;
+  B200W_CHECK_ARG(tiles > 0 && tiles < (1ll << 30), "gemm: tile count out of range");
+  long long g = (32ll << 20) / ((long long)kBM * p.K * 2);
+  p.group_m = (int)(g < 8 ? 8 : (g > 148 ? 148 : g));
+  const int grid = (int)(tiles < device_sm_count() ? tiles : device_sm_count());
+  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  B200W_LAUNCH_OK();
+  count_launch();
+  return kOk;
+}
+
+int gemm_block_n(int n_batch, int rows_per_batch, int n_store) {
+  const long long m_tiles = (long long)n_batch * ceil_div(rows_per_batch, kBM);
+  // few row tiles (decode steps): narrow N tiles so that enough CTAs stream the weights
+  if (m_tiles <= 2) return (n_store % 64 == 0 || n_store > 4096) ? 64 : 32;
+  if (n_store % 256 == 0 && m_tiles * (n_store / 256) >= 2 * 148) return 256;
+  return 128;
+}
+
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int block_n, cudaStream_t stream) {
+  B200W_CHECK_ARG(p.K > 0 && p.K % 8 == 0, "gemm: K must be a positive multiple of 8 (got %d)", p.K);
+  B200W_CHECK_ARG(p.n_store > 0 && p.ldc >= ((p.n_store + 31) / 32) * 32, "gemm: ldc %lld too small for n_store %d",
+                  p.ldc, p.n_store);
+  B200W_CHECK_ARG(p.bias == nullptr || p.n_store % 32 == 0, "gemm: bias needs N %% 32 == 0");
+  switch (block_n) {
+    case 256: return launch_gemm_bn<256>(ta, tb, p, stream);
+    case 128: return launch_gemm_bn<128>(ta, tb, p, stream);
+    case 64: return launch_gemm_bn<64>(ta, tb, p, stream);
+    case 32: return launch_gemm_bn<32>(ta, tb, p, stream);
+    default: set_last_error("gemm: unsupported block_n %d", block_n); return kErrInvalidArgument;
+  }
+}
+
+// Tensor map for the weight operand W (N, K) row-major bf16, box (64, block_n).
+int make_tmap_w(CUtensorMap* out, const void* w, int N, int K, int block_n) {
+  uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, 1};
+  uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)K * 2 * (uint64_t)N};
+  uint32_t box[3] = {kBK, (uint32_t)block_n, 1};
+  return encode_tmap_bf16(out, w, 3, dims, strides, box);
+}
+
+// Tensor map for the activation operand: `n_batch` slabs, each `rows` logical rows of K contiguous bf16,
+// consecutive rows `row_stride` elements apart, slabs `batch_stride` elements apart; box (64, 128, 1).
+int make_tmap_a(CUtensorMap* out, const void* a, int n_batch, int rows, int K, long long row_stride,
+                long long batch_stride) {
+  uint64_t dims[3] = {(uint64_t)K, (uint64_t)rows, (uint64_t)n_batch};
+  uint64_t strides[2] = {(uint64_t)row_stride * 2, (uint64_t)batch_stride * 2};
+  uint32_t box[3] = {kBK, kBM, 1};
+  return encode_tmap_bf16(out, a, 3, dims, strides, box);
+}
+
+}  // namespace b200w

@@ -1,0 +1,77 @@
+// Internal launcher prototypes shared between the kernel translation units and the C-ABI layer.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200_whisper.h"
+
+namespace b200w {
+
+// one-time cudaFuncSetAttribute opt-ins (called eagerly by b200w_model_create, lazily by the launchers)
+int init_gemm();
+int init_attention();
+int init_logmel();
+
+// ---------------------------------------------------------------------------------------- K1 log-mel
+int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
+                  int n_mels, const float* hann, const float* tw400, const int* mel_lo, const int* mel_cnt,
+                  const int* mel_off, const float* mel_w, float* out_unclamped, float* gmax, cudaStream_t stream);
+int launch_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, cudaStream_t stream);
+int launch_mel_windows(const float* mel, const float* gmax, const long long* row0, const int* size, const int* gidx,
+                       int n_windows, int n_mels, __nv_bfloat16* dst, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------- K5 GEMM
+struct GemmParams {
+  int n_batch;         // independent row slabs (M tiles never straddle slabs)
+  int rows_per_batch;  // logical rows per slab; logical row = b * rows_per_batch + t
+  long long out_batch_rows;  // storage rows between slabs of the output (0: rows_per_batch)
+  int N;               // logical output columns (weights rows)
+  int K;
+  int n_store;         // columns stored (whole 32-column chunks starting below n_store are written)
+  void* out;           // bf16 or f32, row-major with leading dimension ldc
+  long long ldc;
+  int out_f32;
+  const float* bias;   // [N] or null
+  const float* resid;  // f32 added after the activation, or null; row = out_row % resid_mod (0: out_row)
+  long long resid_ld;
+  int resid_mod;
+  int gelu;
+  // filled by the launcher
+  int tiles_m_per_batch, tiles_n, group_m;
+};
+
+int gemm_block_n(int n_batch, int rows_per_batch, int n_store);
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int block_n, cudaStream_t stream);
+int make_tmap_w(CUtensorMap* out, const void* w, int N, int K, int block_n);
+int make_tmap_a(CUtensorMap* out, const void* a, int n_batch, int rows, int K, long long row_stride,
+                long long batch_stride);
+
+// ---------------------------------------------------------------------------------------- K4 / K10 / K9
+int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
+                     float* out_f32, cudaStream_t stream);
+int launch_embed(const int* tokens, int tokens_ld, const int* pos, int n_seq, int n_q, const __nv_bfloat16* tok_emb,
+                 const __nv_bfloat16* pos_emb, int d, int n_ctx, float* x, cudaStream_t stream);
+
+using FilterParams = b200w_filter_params;
+int launch_filter_argmax(const float* logits, const uint32_t* suppress_bits, int* tokens, int* n_tokens, int* pos,
+                         float* sum_logprob, int* finished, int n_seq, const FilterParams& fp, cudaStream_t stream);
+int launch_no_speech(const float* logits, int logits_ld, int n_seq, int n_vocab, int no_speech, float* out,
+                     cudaStream_t stream);
+int launch_language(const float* logits, int logits_ld, int n_seq, int lang_begin, int n_lang, int* lang_token,
+                    float* lang_probs, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------- K6 / K7 / K8 attention
+int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n_head, __nv_bfloat16* out,
+                             cudaStream_t stream);
+// self attention over the paged cache: appends this step's k/v rows (taken from qkv) at pos[b] + qi first.
+int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, int n_head, const int* pos,
+                                  __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, const int* block_table,
+                                  int max_pages_per_seq, int page_size, __nv_bfloat16* out, cudaStream_t stream);
+int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, int n_head,
+                                   const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
+                                   __nv_bfloat16* out, cudaStream_t stream);
+
+}  // namespace b200w

@@ -1,0 +1,313 @@
+"""Long-form driver: host mirror of `mlx_whisper/transcribe.py::transcribe` (UPSTREAM; the function
+`./run` reaches through the `mlx_whisper` console script, /root/reference/run:3-6; restated in SURVEY.md
+section 3.1 and A.5).
+
+Same signature, option names, thresholds and result dictionary.  Two execution modes:
+
+* exact (default): the reference's sequential seek loop -- one 30 s window at a time, the next window
+  starts at the last decoded timestamp.  Bit-for-bit the reference control flow.
+* fixed-window batches (`window_batch=N`): the file is cut into back-to-back 30 s windows which are
+  independent when `condition_on_previous_text=False` (the `./run` setting); N windows are encoded and
+  decoded together.  This is the throughput mode the benchmarks measure; segment
+  boundaries can differ from exact mode because the seek does not follow the decoded timestamps.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .audio import FRAMES_PER_SECOND, HOP_LENGTH, N_FRAMES, N_SAMPLES, SAMPLE_RATE, _to_device_audio, log_mel_unclamped
+from .decoding import DecodingOptions, DecodingResult, DecodingTask, detect_language
+from .load_models import load_model
+from .tokenizer import LANGUAGES, get_tokenizer
+
+
+def _format_timestamp(seconds: float):
+    assert seconds >= 0, "non-negative timestamp expected"
+    milliseconds = round(seconds * 1000.0)
+    hours = milliseconds // 3_600_000
+    milliseconds -= hours * 3_600_000
+    minutes = milliseconds // 60_000
+    milliseconds -= minutes * 60_000
+    seconds = milliseconds // 1_000
+    milliseconds -= seconds * 1_000
+    hours_marker = f"{hours:02d}:" if hours > 0 else ""
+    return f"{hours_marker}{minutes:02d}:{seconds:02d}.{milliseconds:03d}"
+
+
+class ModelHolder:
+    """One cached model per process, like the reference (not re-entrant)."""
+
+    model = None
+    model_path = None
+
+    @classmethod
+    def get_model(cls, model_path: str, dtype=torch.bfloat16):
+        if cls.model is None or model_path != cls.model_path:
+            cls.model = load_model(model_path, dtype=dtype)
+            cls.model_path = model_path
+        return cls.model
+
+
+def _segments_for_window(tokens: np.ndarray, seek: int, segment_size: int, result: DecodingResult, tokenizer,
+                         input_stride: int, time_precision: float, follow_timestamps: bool):
+    """Split one window's tokens at consecutive timestamp pairs.  Returns (segments, seek advance)."""
+    time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
+    segment_duration = segment_size * HOP_LENGTH / SAMPLE_RATE
+
+    def new_segment(*, start: float, end: float, toks, res: DecodingResult):
+        toks = [int(t) for t in toks]
+        text_tokens = [t for t in toks if t < tokenizer.eot]
+        return {"seek": seek, "start": start, "end": end, "text": tokenizer.decode(text_tokens), "tokens": toks,
+                "temperature": res.temperature, "avg_logprob": res.avg_logprob,
+                "compression_ratio": res.compression_ratio, "no_speech_prob": res.no_speech_prob}
+
+    current_segments = []
+    timestamp_tokens = tokens >= tokenizer.timestamp_begin
+    single_timestamp_ending = timestamp_tokens[-2:].tolist() == [False, True]
+    consecutive = np.where(np.logical_and(timestamp_tokens[:-1], timestamp_tokens[1:]))[0]
+    consecutive += 1
+    if len(consecutive) > 0:
+        slices = consecutive.tolist()
+        if single_timestamp_ending:
+            slices.append(len(tokens))
+        last_slice = 0
+        for current_slice in slices:
+            sliced_tokens = tokens[last_slice:current_slice]
+            start_timestamp_pos = int(sliced_tokens[0]) - tokenizer.timestamp_begin
+            end_timestamp_pos = int(sliced_tokens[-1]) - tokenizer.timestamp_begin
+            current_segments.append(new_segment(start=time_offset + start_timestamp_pos * time_precision,
+                                                end=time_offset + end_timestamp_pos * time_precision,
+                                                toks=sliced_tokens, res=result))
+            last_slice = current_slice
+        if single_timestamp_ending or not follow_timestamps:
+            # single timestamp at the end means no speech after the last timestamp
+            advance = segment_size
+        else:
+            # otherwise, ignore the unfinished segment and seek to the last timestamp
+            last_timestamp_pos = int(tokens[last_slice - 1]) - tokenizer.timestamp_begin
+            advance = last_timestamp_pos * input_stride
+    else:
+        duration = segment_duration
+        timestamps = tokens[timestamp_tokens.nonzero()[0]]
+        if len(timestamps) > 0 and timestamps[-1] != tokenizer.timestamp_begin:
+            # no consecutive timestamps but it has a timestamp; use the last one
+            last_timestamp_pos = int(timestamps[-1]) - tokenizer.timestamp_begin
+            duration = last_timestamp_pos * time_precision
+        current_segments.append(new_segment(start=time_offset, end=time_offset + duration, toks=tokens, res=result))
+        advance = segment_size
+    # if a segment is instantaneous or does not contain text, clear it
+    for segment in current_segments:
+        if segment["start"] == segment["end"] or segment["text"].strip() == "":
+            segment["text"] = ""
+            segment["tokens"] = []
+    return current_segments, advance
+
+
+def transcribe(
+    audio: Union[str, np.ndarray, torch.Tensor],
+    *,
+    path_or_hf_repo: str = "mlx-community/whisper-tiny",
+    verbose: Optional[bool] = None,
+    temperature: Union[float, Tuple[float, ...]] = (0.0, 0.2, 0.4, 0.6, 0.8, 1.0),
+    compression_ratio_threshold: Optional[float] = 2.4,
+    logprob_threshold: Optional[float] = -1.0,
+    no_speech_threshold: Optional[float] = 0.6,
+    condition_on_previous_text: bool = True,
+    initial_prompt: Optional[str] = None,
+    word_timestamps: bool = False,
+    prepend_punctuations: str = "\"'“¿([{-",
+    append_punctuations: str = "\"'.。,，!！?？:：”)]}、",
+    clip_timestamps: Union[str, List[float]] = "0",
+    hallucination_silence_threshold: Optional[float] = None,
+    window_batch: Optional[int] = None,
+    encoder_batch: int = 32,
+    model=None,
+    **decode_options,
+):
+    """Transcribe an audio file (path, NumPy array or torch tensor of 16 kHz mono samples).
+
+    Returns {"text": str, "segments": [...], "language": str} exactly like the reference.  Extra keyword
+    arguments (not in the reference): `window_batch` selects the fixed-window batched mode (module
+    docstring; default from $B200W_WINDOW_BATCH, else exact sequential mode), `encoder_batch` bounds how
+    many windows go through one encoder call, `model` passes an already loaded `Whisper`.
+    """
+    if word_timestamps:
+        raise NotImplementedError("word_timestamps is not implemented yet (it is not on the `./run` path)")
+    if hallucination_silence_threshold is not None and verbose:
+        warnings.warn("--hallucination_silence_threshold requires --word_timestamps True; it has no effect")
+
+    dtype = torch.bfloat16 if decode_options.get("fp16", True) else torch.float32
+    if model is None:
+        model = ModelHolder.get_model(path_or_hf_repo, dtype)
+    if window_batch is None:
+        window_batch = int(os.environ.get("B200W_WINDOW_BATCH", "0"))
+
+    # whole-file log-mel with 30 s of zero padding; the clamp uses the file-wide maximum (K1 + K1b)
+    pcm = _to_device_audio(audio, model.device)
+    if pcm.ndim != 1:
+        raise ValueError("transcribe() takes one mono signal")
+    mel, gmax = log_mel_unclamped(pcm, n_mels=model.dims.n_mels, padding=N_SAMPLES)
+    mel2d = mel[0]
+    content_frames = mel2d.shape[-2] - N_FRAMES
+    content_duration = float(content_frames * HOP_LENGTH / SAMPLE_RATE)
+
+    def slabs_for(seeks: List[int], sizes: List[int]) -> torch.Tensor:
+        return model.mel_windows(mel2d, gmax, seeks, sizes, [0] * len(seeks))
+
+    if decode_options.get("language", None) is None:
+        if not model.is_multilingual:
+            decode_options["language"] = "en"
+        else:
+            if verbose:
+                print("Detecting language using up to the first 30 seconds. Use the `language` decoding option to specify the language")
+            xa0 = model.encode_slabs(slabs_for([0], [min(N_FRAMES, mel2d.shape[-2])]))
+            _, probs = detect_language(model, xa0)
+            decode_options["language"] = max(probs[0], key=probs[0].get)
+            if verbose is not None:
+                print(f"Detected language: {LANGUAGES[decode_options['language']].title()}")
+
+    language: str = decode_options["language"]
+    task: str = decode_options.get("task", "transcribe")
+    tokenizer = get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language=language, task=task,
+                              vocab_dir=getattr(model, "model_path", None))
+
+    if isinstance(clip_timestamps, str):
+        clip_timestamps = [float(ts) for ts in (clip_timestamps.split(",") if clip_timestamps else [])]
+    seek_points: List[int] = [round(ts * FRAMES_PER_SECOND) for ts in clip_timestamps]
+    if len(seek_points) == 0:
+        seek_points.append(0)
+    if len(seek_points) % 2 == 1:
+        seek_points.append(content_frames)
+    else:
+        seek_points[-1] = min(content_frames, seek_points[-1])
+    seek_clips: List[Tuple[int, int]] = list(zip(seek_points[::2], seek_points[1::2]))
+
+    temperatures = [temperature] if isinstance(temperature, (int, float)) else list(temperature)
+
+    def needs_fallback(res: DecodingResult) -> bool:
+        fallback = False
+        if compression_ratio_threshold is not None and res.compression_ratio > compression_ratio_threshold:
+            fallback = True  # too repetitive
+        if logprob_threshold is not None and res.avg_logprob < logprob_threshold:
+            fallback = True  # average log probability is too low
+        if no_speech_threshold is not None and res.no_speech_prob > no_speech_threshold:
+            fallback = False  # silence
+        return fallback
+
+    def options_for(t: float, prompt) -> DecodingOptions:
+        kwargs = {**decode_options}
+        if t > 0:
+            kwargs.pop("beam_size", None)  # disable beam_size and patience when t > 0
+            kwargs.pop("patience", None)
+        else:
+            kwargs.pop("best_of", None)  # disable best_of when t == 0
+        kwargs.pop("fp16", None)
+        return DecodingOptions(**kwargs, prompt=prompt, temperature=t)
+
+    def decode_with_fallback(features: torch.Tensor, prompt) -> List[DecodingResult]:
+        """features (n, 1500, d): every window is retried at the next temperature until it passes."""
+        n = features.shape[0]
+        results: List[Optional[DecodingResult]] = [None] * n
+        pending = list(range(n))
+        for t in temperatures:
+            out = DecodingTask(model, options_for(float(t), prompt)).run_features(features[pending])
+            still = []
+            for i, r in zip(pending, out):
+                results[i] = r
+                if needs_fallback(r):
+                    still.append(i)
+            pending = still
+            if not pending:
+                break
+        return results
+
+    input_stride = N_FRAMES // model.dims.n_audio_ctx  # mel frames per output token: 2
+    time_precision = input_stride * HOP_LENGTH / SAMPLE_RATE  # time per output token: 0.02 (seconds)
+    all_tokens: List[int] = []
+    all_segments: List[dict] = []
+    prompt_reset_since = 0
+    if initial_prompt is not None:
+        initial_prompt_tokens = tokenizer.encode(" " + initial_prompt.strip())
+        all_tokens.extend(initial_prompt_tokens)
+    else:
+        initial_prompt_tokens = []
+
+    def should_skip(res: DecodingResult) -> bool:
+        if no_speech_threshold is None:
+            return False
+        skip = res.no_speech_prob > no_speech_threshold
+        if logprob_threshold is not None and res.avg_logprob > logprob_threshold:
+            skip = False  # don't skip if the logprob is high enough, despite the no_speech_prob
+        return skip
+
+    def emit(current_segments: List[dict]):
+        if verbose:
+            for segment in current_segments:
+                print(f"[{_format_timestamp(segment['start'])} --> {_format_timestamp(segment['end'])}] {segment['text']}")
+        all_segments.extend({"id": i, **segment} for i, segment in enumerate(current_segments, start=len(all_segments)))
+        all_tokens.extend(token for segment in current_segments for token in segment["tokens"])
+
+    batched = window_batch > 0 and not condition_on_previous_text and initial_prompt is None
+    if window_batch > 0 and not batched and verbose:
+        warnings.warn("window_batch needs condition_on_previous_text=False and no initial_prompt; using exact mode")
+
+    if batched:
+        # ---------------- fixed 30 s windows, window_batch at a time ----------------
+        windows: List[Tuple[int, int]] = []
+        for clip_start, clip_end in seek_clips:
+            s = clip_start
+            while s < clip_end:
+                size = min(N_FRAMES, content_frames - s, clip_end - s)
+                if size <= 0:
+                    break
+                windows.append((s, size))
+                s += size
+        for i0 in range(0, len(windows), window_batch):
+            chunk = windows[i0: i0 + window_batch]
+            feats = []
+            for e0 in range(0, len(chunk), encoder_batch):
+                sub = chunk[e0: e0 + encoder_batch]
+                feats.append(model.encode_slabs(slabs_for([w[0] for w in sub], [w[1] for w in sub])))
+            features = torch.cat(feats, 0) if len(feats) > 1 else feats[0]
+            results = decode_with_fallback(features, [])
+            for (seek, size), res in zip(chunk, results):
+                if should_skip(res):
+                    continue
+                tokens = np.array(res.tokens, dtype=np.int64)
+                segs, _ = _segments_for_window(tokens, seek, size, res, tokenizer, input_stride, time_precision, False)
+                emit(segs)
+    else:
+        # ---------------- exact mode: the reference's sequential seek loop ----------------
+        clip_idx = 0
+        seek = seek_clips[0][0]
+        while clip_idx < len(seek_clips):
+            seek_clip_start, seek_clip_end = seek_clips[clip_idx]
+            if seek < seek_clip_start:
+                seek = seek_clip_start
+            if seek >= seek_clip_end:
+                clip_idx += 1
+                if clip_idx < len(seek_clips):
+                    seek = seek_clips[clip_idx][0]
+                continue
+            segment_size = min(N_FRAMES, content_frames - seek, seek_clip_end - seek)
+            features = model.encode_slabs(slabs_for([seek], [segment_size]))
+            result = decode_with_fallback(features, all_tokens[prompt_reset_since:])[0]
+            tokens = np.array(result.tokens, dtype=np.int64)
+            if should_skip(result):
+                seek += segment_size  # fast-forward to the next segment boundary
+                continue
+            segs, advance = _segments_for_window(tokens, seek, segment_size, result, tokenizer, input_stride,
+                                                 time_precision, True)
+            seek += advance
+            emit(segs)
+            if not condition_on_previous_text or result.temperature > 0.5:
+                # do not feed the prompt tokens if a high temperature was used
+                prompt_reset_since = len(all_tokens)
+
+    return dict(text=tokenizer.decode(all_tokens[len(initial_prompt_tokens):]), segments=all_segments, language=language)
