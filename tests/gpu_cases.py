@@ -217,10 +217,10 @@ def case_layernorm_embed():
     for d in (384, 768, 1280):
         x = torch.randn(777, d, generator=g) * 3 + 1
         gm, bt = torch.randn(d, generator=g), torch.randn(d, generator=g)
-        xc = x.cuda()
+        xc, gc, bc = x.cuda(), gm.cuda(), bt.cuda()  # keep references: a temporary's memory may be reused
         ob = torch.empty((777, d), dtype=torch.bfloat16, device="cuda")
         of = torch.empty((777, d), dtype=torch.float32, device="cuda")
-        L.check(lib.b200w_layernorm(L.ptr(xc), L.ptr(gm.cuda()), L.ptr(bt.cuda()), 777, d, L.ptr(ob), L.ptr(of), L.stream()))
+        L.check(lib.b200w_layernorm(L.ptr(xc), L.ptr(gc), L.ptr(bc), 777, d, L.ptr(ob), L.ptr(of), L.stream()))
         torch.cuda.synchronize()
         ref = torch.nn.functional.layer_norm(x, (d,), gm, bt, eps=1e-5)
         e32 = (of.cpu() - ref).abs().max().item()
@@ -233,7 +233,8 @@ def case_layernorm_embed():
     toks = torch.randint(0, V, (5, 456), generator=g, dtype=torch.int32)
     pos = torch.tensor([0, 3, 7, 100, 440], dtype=torch.int32)
     x = torch.empty((5 * 2, d), dtype=torch.float32, device="cuda")
-    L.check(lib.b200w_embed(L.ptr(toks.cuda()), 456, L.ptr(pos.cuda()), 5, 2, L.ptr(te.cuda()), L.ptr(pe.cuda()), d, n_ctx,
+    toks_c, pos_c, te_c, pe_c = toks.cuda(), pos.cuda(), te.cuda(), pe.cuda()
+    L.check(lib.b200w_embed(L.ptr(toks_c), 456, L.ptr(pos_c), 5, 2, L.ptr(te_c), L.ptr(pe_c), d, n_ctx,
                             L.ptr(x), L.stream()))
     torch.cuda.synchronize()
     ref = torch.stack([te[toks[b, pos[b] + q].long()].float() + pe[(pos[b] + q).long()].float() for b in range(5) for q in range(2)])
@@ -302,9 +303,9 @@ def case_decoder_attention():
                 vp[pg, j % ps] = hist_v[b, j]
         qkv = _bf16(torch.randn(B, n_q, 3 * d, generator=g))
         o = torch.empty((B, n_q, d), dtype=torch.bfloat16, device="cuda")
-        kpc, vpc = kp.cuda(), vp.cuda()
-        L.check(lib.b200w_decoder_self_attention(L.ptr(qkv.cuda()), B, n_q, H, L.ptr(pos.cuda()), L.ptr(kpc), L.ptr(vpc),
-                                                 L.ptr(bt.cuda()), max_pages, ps, L.ptr(o), L.stream()))
+        kpc, vpc, qkv_c, pos_c, bt_c = kp.cuda(), vp.cuda(), qkv.cuda(), pos.cuda(), bt.cuda()
+        L.check(lib.b200w_decoder_self_attention(L.ptr(qkv_c), B, n_q, H, L.ptr(pos_c), L.ptr(kpc), L.ptr(vpc),
+                                                 L.ptr(bt_c), max_pages, ps, L.ptr(o), L.stream()))
         torch.cuda.synchronize()
         errs = []
         for b in range(B):
@@ -328,8 +329,9 @@ def case_decoder_attention():
         ckv = _bf16(torch.randn(n_slots, T, 2 * d, generator=g))
         q = _bf16(torch.randn(B, n_q, d, generator=g))
         o = torch.empty((B, n_q, d), dtype=torch.bfloat16, device="cuda")
-        L.check(lib.b200w_decoder_cross_attention(L.ptr(q.cuda()), B, n_q, H, L.ptr(ckv.cuda()), T * 2 * d, T,
-                                                  L.ptr(slot.cuda()), L.ptr(o), L.stream()))
+        q_c, ckv_c, slot_c = q.cuda(), ckv.cuda(), slot.cuda()
+        L.check(lib.b200w_decoder_cross_attention(L.ptr(q_c), B, n_q, H, L.ptr(ckv_c), T * 2 * d, T,
+                                                  L.ptr(slot_c), L.ptr(o), L.stream()))
         torch.cuda.synchronize()
         kv = ckv[slot.long()].float()
         ref = _sdpa_ref(q.float(), kv[..., :d], kv[..., d:], H)

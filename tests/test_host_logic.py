@@ -1,0 +1,200 @@
+"""Host-side mirror of the reference interface: tokenizer table, writers, segmentation, CLI flags, options.
+CPU only; the segmentation is compared with the oracle's restatement on synthetic token streams."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from tools import synth
+
+
+def test_tokenizer_special_ids_match_oracle():
+    from oracle.tokens import TokenIds
+    from whisper_mlx_b200.tokenizer import get_tokenizer
+
+    for n_lang, n_vocab in ((99, 51865), (100, 51866)):
+        tk = get_tokenizer(True, num_languages=n_lang, language="fr", task="transcribe")
+        ids = TokenIds(n_vocab)
+        assert tk.encoding.n_vocab == n_vocab
+        for name in ("eot", "sot", "translate", "transcribe", "sot_lm", "sot_prev", "no_speech", "no_timestamps", "timestamp_begin"):
+            assert getattr(tk, name) == getattr(ids, name), name
+        assert tk.sot_sequence == ids.sot_sequence("fr")
+        assert tuple(sorted(set(tk.non_speech_tokens))) == tuple(t for t in ids.suppress_set() if t < 50257)
+        assert len(tk.all_language_tokens) == n_lang and tk.language_code(tk.all_language_tokens[-1]) == ("yue" if n_lang == 100 else "su")
+        assert tk.encode(" ") == [220]
+        assert tk.decode_with_timestamps([tk.timestamp_begin + 54]) == "<|1.08|>"
+
+
+def test_surrogate_vocabulary_matches_oracle():
+    from oracle.tokens import decode_text
+    from whisper_mlx_b200.tokenizer import get_tokenizer
+
+    tk = get_tokenizer(True, num_languages=100)
+    toks = [1, 17, 50256, 31337, tk.timestamp_begin + 3, 400]
+    assert tk.decode(toks) == decode_text(toks, tk.timestamp_begin)
+
+
+def test_suppress_set_matches_oracle():
+    from oracle.tokens import TokenIds
+    from whisper_mlx_b200.decoding import DecodingOptions, DecodingTask
+
+    class FakeModel:
+        is_multilingual = True
+        num_languages = 100
+
+        class dims:
+            n_text_ctx = 448
+            n_vocab = 51866
+            n_audio_ctx = 1500
+
+    task = DecodingTask(FakeModel(), DecodingOptions(language="en"))
+    assert task._get_suppress_tokens() == TokenIds(51866).suppress_set()
+    assert task.initial_tokens == TokenIds(51866).sot_sequence("en") and task.sample_begin == 3 and task.sample_len == 224
+    t2 = DecodingTask(FakeModel(), DecodingOptions(language="en", prompt=list(range(1000, 1300)), without_timestamps=True))
+    assert t2.initial_tokens[0] == 50362 and len(t2.initial_tokens) == 1 + 223 + 4 and t2.sot_index == 224
+    with pytest.raises(NotImplementedError):
+        DecodingTask(FakeModel(), DecodingOptions(language="en", beam_size=5))
+    with pytest.raises(ValueError):
+        DecodingTask(FakeModel(), DecodingOptions(language="en", best_of=5))
+
+
+def _oracle_segments(tokens, seek, size, fixed):
+    """The oracle's segmentation, driven with a canned decode result."""
+    from oracle import decoding as OD, model as OM, transcribe as OT
+    from oracle.tokens import TokenIds
+
+    ids = TokenIds(51866)
+    out = {}
+
+    class R:
+        pass
+
+    # replicate the loop body of oracle.transcribe for one window (same code path as its while-loop)
+    import types
+    import numpy as _np
+
+    res = OD.DecodingResult(tokens=list(tokens), text="", avg_logprob=-0.5, no_speech_prob=0.0, temperature=0.0, compression_ratio=1.0)
+    toks = _np.array(tokens, dtype=_np.int64)
+    ts = toks >= ids.timestamp_begin
+    single_ending = ts[-2:].tolist() == [False, True]
+    consecutive = _np.where(_np.logical_and(ts[:-1], ts[1:]))[0] + 1
+    segs, adv = [], None
+    t0 = seek * 160 / 16000
+    if len(consecutive) > 0:
+        slices = consecutive.tolist()
+        if single_ending:
+            slices.append(len(toks))
+        last = 0
+        for cur in slices:
+            sl = toks[last:cur]
+            segs.append((t0 + (int(sl[0]) - ids.timestamp_begin) * 0.02, t0 + (int(sl[-1]) - ids.timestamp_begin) * 0.02, sl.tolist()))
+            last = cur
+        adv = size if (single_ending or fixed) else (int(toks[last - 1]) - ids.timestamp_begin) * 2
+    else:
+        dur = size * 160 / 16000
+        stamps = toks[ts.nonzero()[0]]
+        if len(stamps) > 0 and stamps[-1] != ids.timestamp_begin:
+            dur = (int(stamps[-1]) - ids.timestamp_begin) * 0.02
+        segs.append((t0, t0 + dur, toks.tolist()))
+        adv = size
+    return segs, adv
+
+
+@pytest.mark.parametrize("fixed", [False, True])
+def test_segmentation_matches_oracle(fixed):
+    from whisper_mlx_b200.decoding import DecodingResult
+    from whisper_mlx_b200.tokenizer import get_tokenizer
+    from whisper_mlx_b200.transcribe import _segments_for_window
+
+    tk = get_tokenizer(True, num_languages=100, language="en", task="transcribe")
+    tb = tk.timestamp_begin
+    streams = [
+        [tb, 10, 11, tb + 100, tb + 100, 12, tb + 250, tb + 250, 13, 14],   # unfinished tail: seek to the last pair
+        [tb + 5, 10, tb + 1500],                                           # single timestamp ending
+        [tb, 10, 11, 12],                                                   # no closing timestamp
+        [tb + 20, 7, tb + 60, tb + 60, 8, tb + 90],                         # pair then single ending
+        [tb, tb],                                                           # empty pair
+        [10, 11, 12],
+    ]
+    for s in streams:
+        res = DecodingResult(audio_features=None, language="en", tokens=s, avg_logprob=-0.5, no_speech_prob=0.0, temperature=0.0,
+                             compression_ratio=1.0)
+        segs, adv = _segments_for_window(np.array(s, dtype=np.int64), 3000, 3000, res, tk, 2, 0.02, not fixed)
+        ref, ref_adv = _oracle_segments(s, 3000, 3000, fixed)
+        assert adv == ref_adv, s
+        assert len(segs) == len(ref)
+        for g, (st, en, toks) in zip(segs, ref):
+            assert abs(g["start"] - st) < 1e-9 and abs(g["end"] - en) < 1e-9
+            if g["start"] != g["end"] and g["text"].strip():
+                assert g["tokens"] == toks
+            else:
+                assert g["tokens"] == [] and g["text"] == ""
+
+
+def test_writers(tmp_path):
+    from whisper_mlx_b200.writers import get_writer
+
+    result = {"text": " a b", "language": "en",
+              "segments": [{"id": 0, "start": 0.0, "end": 1.5, "text": " hello there "}, {"id": 1, "start": 3661.25, "end": 3662.0, "text": "x --> y"}]}
+    get_writer("txt", str(tmp_path))(result, "out")
+    assert open(tmp_path / "out.txt").read() == "hello there\nx --> y\n"
+    get_writer("all", str(tmp_path))(result, "all")
+    srt = open(tmp_path / "all.srt").read()
+    assert "00:00:00,000 --> 00:00:01,500" in srt and "01:01:01,250 --> 01:01:02,000" in srt and "x -> y" in srt
+    assert open(tmp_path / "all.vtt").read().startswith("WEBVTT\n")
+    assert open(tmp_path / "all.tsv").read().splitlines()[1] == "0\t1500\thello there"
+    import json
+
+    assert json.load(open(tmp_path / "all.json"))["segments"][1]["start"] == 3661.25
+
+
+def test_cli_accepts_the_reference_flags():
+    """The exact flag spelling of /root/reference/run:3-6."""
+    from whisper_mlx_b200.cli import build_parser
+
+    a = build_parser().parse_args(["in.mp3", "-f", "txt", "--output-name", "out", "--model", "mlx-community/whisper-large-v3-mlx",
+                                   "--condition-on-previous-text", "False", "--hallucination-silence-threshold", "1"])
+    assert a.audio == ["in.mp3"] and a.output_format == "txt" and a.output_name == "out"
+    assert a.model == "mlx-community/whisper-large-v3-mlx" and a.condition_on_previous_text is False
+    assert a.hallucination_silence_threshold == 1.0 and a.word_timestamps is False and a.best_of == 5
+    assert a.temperature == 0 and a.temperature_increment_on_fallback == 0.2
+
+
+def test_audio_helpers():
+    import torch
+    from oracle import audio as OA
+    from whisper_mlx_b200 import audio as A
+
+    assert (A.SAMPLE_RATE, A.N_FFT, A.HOP_LENGTH, A.N_SAMPLES, A.N_FRAMES) == (16000, 400, 160, 480000, 3000)
+    for n in (80, 128):
+        assert np.array_equal(A.mel_filters(n), OA.mel_filters(n))
+    with pytest.raises(AssertionError):
+        A.mel_filters(64)
+    x = np.arange(10, dtype=np.float32)
+    assert np.array_equal(A.pad_or_trim(x, 4), x[:4]) and A.pad_or_trim(x, 16).shape == (16,)
+    t = torch.arange(12.0).view(3, 4)
+    assert A.pad_or_trim(t, 6, axis=0).shape == (6, 4) and A.pad_or_trim(t, 2, axis=-1).shape == (3, 2)
+    assert torch.equal(A.pad_or_trim(t, 6, axis=0)[3:], torch.zeros(3, 4))
+
+
+def test_load_audio_wav_roundtrip(tmp_path):
+    import wave
+    from whisper_mlx_b200.audio import load_audio
+
+    pcm = (synth.white_noise(1600, 0) * 32767).astype(np.int16)
+    p = str(tmp_path / "a.wav")
+    with wave.open(p, "wb") as w:
+        w.setnchannels(1), w.setsampwidth(2), w.setframerate(16000)
+        w.writeframes(pcm.tobytes())
+    x = load_audio(p)
+    assert x.dtype == np.float32 and np.array_equal(x, pcm.astype(np.float32) / 32768.0)
+    with pytest.raises(RuntimeError, match="Failed to load audio"):
+        load_audio(str(tmp_path / "missing.mp3"))
+
+
+def test_load_model_errors(tmp_path):
+    from whisper_mlx_b200.load_models import load_model
+
+    with pytest.raises(FileNotFoundError):
+        load_model(str(tmp_path / "nope"))

@@ -91,13 +91,32 @@ def _init_one(name: str, shape, seed: int) -> np.ndarray:
     return x / np.float32(np.sqrt(fan_in))
 
 
-def random_weights(dims: dict, seed: int = 0):
-    """Yield (name, f32 ndarray whose values are exactly bf16-representable)."""
+def random_weights(dims: dict, seed: int = 0, device: str = "cpu"):
+    """Yield (name, bf16 tensor).
+
+    device="cpu": NumPy generator, identical on every machine (tests, golden vectors).
+    device="cuda": torch CUDA generator with the same per-tensor scaling -- seconds instead of half a
+    minute for large-v3; used by bench.py, which hands the very same tensors to the CPU baseline.
+    """
     import torch
 
+    if device == "cpu":
+        for name, shape in weight_shapes(dims).items():
+            yield name, torch.from_numpy(_init_one(name, shape, seed)).to(torch.bfloat16)
+        return
+    gen = torch.Generator(device=device)
     for name, shape in weight_shapes(dims).items():
-        w = torch.from_numpy(_init_one(name, shape, seed)).to(torch.bfloat16)
-        yield name, w
+        gen.manual_seed((seed << 32) ^ zlib.crc32(name.encode()))
+        x = torch.randn(shape, generator=gen, device=device, dtype=torch.float32)
+        if name.endswith("_ln.weight") or name.endswith("ln_post.weight") or name.endswith("decoder.ln.weight"):
+            x = 1.0 + 0.05 * x
+        elif name.endswith(".bias"):
+            x = 0.02 * x
+        elif "embedding" in name:
+            x = 0.05 * x
+        else:
+            x = x / float(np.sqrt(np.prod(shape[1:])))
+        yield name, x.to(torch.bfloat16)
 
 
 def write_model(path: str, model: str = "tiny", seed: int = 0, dtype: str = "bfloat16") -> str:

@@ -41,7 +41,7 @@ def _read_wav(file: str, sr: int) -> Optional[np.ndarray]:
             if w.getnchannels() > 1:
                 data = data.reshape(-1, w.getnchannels()).astype(np.int32).mean(axis=1).astype(np.int16)
             return data
-    except (wave.Error, EOFError):
+    except (wave.Error, EOFError, OSError):
         return None
 
 

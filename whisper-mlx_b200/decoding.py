@@ -23,6 +23,15 @@ from .audio import CHUNK_LENGTH, N_FRAMES
 from .tokenizer import Tokenizer, get_tokenizer
 
 
+# kernels launched through CUDA-graph replays (these bypass the library's own launch counter);
+# total kernels = b200w_launch_count() + GRAPH_KERNEL_LAUNCHES
+GRAPH_KERNEL_LAUNCHES = 0
+
+
+def total_kernel_launches() -> int:
+    return int(_lib.load().b200w_launch_count()) + GRAPH_KERNEL_LAUNCHES
+
+
 def compression_ratio(text) -> float:
     text_bytes = text.encode("utf-8")
     return len(text_bytes) / len(zlib.compress(text_bytes))
@@ -157,14 +166,19 @@ class DecodeSession:
 
     def sample_step(self) -> None:
         """One single-token step + token selection, replayed from a CUDA graph after the first capture."""
+        global GRAPH_KERNEL_LAUNCHES
         with torch.cuda.device(self.model.device):
             if self._graph is None:
                 self._workspace(1)
+                before = self.lib.b200w_launch_count()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._step(1, -1, True)
                 self._graph = g
+                self._graph_kernels = self.lib.b200w_launch_count() - before
+                GRAPH_KERNEL_LAUNCHES -= self._graph_kernels  # the capture itself launched nothing
             self._graph.replay()
+            GRAPH_KERNEL_LAUNCHES += self._graph_kernels
 
 
 class DecodingTask:

@@ -24,6 +24,7 @@ import torch
 from .audio import FRAMES_PER_SECOND, HOP_LENGTH, N_FRAMES, N_SAMPLES, SAMPLE_RATE, _to_device_audio, log_mel_unclamped
 from .decoding import DecodingOptions, DecodingResult, DecodingTask, detect_language
 from .load_models import load_model
+from .sharding import gather_by_index, plan_windows, shard_indices
 from .tokenizer import LANGUAGES, get_tokenizer
 
 
@@ -128,6 +129,8 @@ def transcribe(
     window_batch: Optional[int] = None,
     encoder_batch: int = 32,
     model=None,
+    rank: int = 0,
+    world_size: int = 1,
     **decode_options,
 ):
     """Transcribe an audio file (path, NumPy array or torch tensor of 16 kHz mono samples).
@@ -135,7 +138,10 @@ def transcribe(
     Returns {"text": str, "segments": [...], "language": str} exactly like the reference.  Extra keyword
     arguments (not in the reference): `window_batch` selects the fixed-window batched mode (module
     docstring; default from $B200W_WINDOW_BATCH, else exact sequential mode), `encoder_batch` bounds how
-    many windows go through one encoder call, `model` passes an already loaded `Whisper`.
+    many windows go through one encoder call, `model` passes an already loaded `Whisper`; `rank` /
+    `world_size` (batched mode, one process per GPU with torch.distributed initialised) make this process
+    decode only its block of windows and gather the per-window segments on the host, so every rank returns
+    the full result.
     """
     if word_timestamps:
         raise NotImplementedError("word_timestamps is not implemented yet (it is not on the `./run` path)")
@@ -254,33 +260,36 @@ def transcribe(
         all_tokens.extend(token for segment in current_segments for token in segment["tokens"])
 
     batched = window_batch > 0 and not condition_on_previous_text and initial_prompt is None
+    if world_size > 1 and not batched:
+        raise ValueError("sharding over ranks needs the fixed-window mode (window_batch > 0, "
+                         "condition_on_previous_text=False, no initial_prompt): exact mode is sequential per file")
     if window_batch > 0 and not batched and verbose:
         warnings.warn("window_batch needs condition_on_previous_text=False and no initial_prompt; using exact mode")
 
     if batched:
         # ---------------- fixed 30 s windows, window_batch at a time ----------------
-        windows: List[Tuple[int, int]] = []
-        for clip_start, clip_end in seek_clips:
-            s = clip_start
-            while s < clip_end:
-                size = min(N_FRAMES, content_frames - s, clip_end - s)
-                if size <= 0:
-                    break
-                windows.append((s, size))
-                s += size
-        for i0 in range(0, len(windows), window_batch):
-            chunk = windows[i0: i0 + window_batch]
+        windows = plan_windows(content_frames, seek_clips, N_FRAMES)
+        mine = shard_indices(len(windows), rank, world_size)  # all windows when world_size == 1
+        local = {}
+        for i0 in range(0, len(mine), window_batch):
+            idxs = mine[i0: i0 + window_batch]
+            chunk = [windows[i] for i in idxs]
             feats = []
             for e0 in range(0, len(chunk), encoder_batch):
                 sub = chunk[e0: e0 + encoder_batch]
                 feats.append(model.encode_slabs(slabs_for([w[0] for w in sub], [w[1] for w in sub])))
             features = torch.cat(feats, 0) if len(feats) > 1 else feats[0]
             results = decode_with_fallback(features, [])
-            for (seek, size), res in zip(chunk, results):
+            for i, (seek, size), res in zip(idxs, chunk, results):
                 if should_skip(res):
+                    local[i] = None
                     continue
                 tokens = np.array(res.tokens, dtype=np.int64)
                 segs, _ = _segments_for_window(tokens, seek, size, res, tokenizer, input_stride, time_precision, False)
+                local[i] = segs
+        # host-side gather of the per-window segments (no device collective on the data path)
+        for segs in gather_by_index(local, len(windows)) if world_size > 1 else [local[i] for i in range(len(windows))]:
+            if segs is not None:
                 emit(segs)
     else:
         # ---------------- exact mode: the reference's sequential seek loop ----------------
