@@ -255,7 +255,8 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_q, in
   __shared__ float s_q[kHd];
   __shared__ float s_p[kMaxSelfKeys];
   __shared__ float s_red[kSelfThreads / 32];
-  __shared__ float s_acc[2][kHd];
+  __shared__ float s_acc[kSelfThreads / 32][kHd];
+  __shared__ int s_bt[kMaxSelfKeys / 8];
 
   const int h = blockIdx.x, b = blockIdx.y, qi = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -264,39 +265,41 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_q, in
   const int n_keys = p0 + qi + 1;    // causal
   const long long my_row = ((long long)b * n_q + qi) * 3 * d;
 
+  if (tid < max_pages) s_bt[tid] = block_table[b * max_pages + tid];
+  if (tid >= 64) s_q[tid - 64] = __bfloat162float(qkv[my_row + h * kHd + tid - 64]) * (0.125f * kLog2e);
+  __syncthreads();
+
   // append this token's k / v rows to the paged cache (each (b, h, qi) block owns its 64-wide slice)
   if (tid < 16) {
     const int j = p0 + qi;
-    const int page = block_table[b * max_pages + j / page_size];
-    const long long dst = ((long long)page * page_size + j % page_size) * d + h * kHd;
+    const long long dst = ((long long)s_bt[j / page_size] * page_size + j % page_size) * d + h * kHd;
     const uint4* ks = reinterpret_cast<const uint4*>(qkv + my_row + d + h * kHd);
     const uint4* vs = reinterpret_cast<const uint4*>(qkv + my_row + 2 * d + h * kHd);
     if (tid < 8) reinterpret_cast<uint4*>(k_pages + dst)[tid] = ks[tid];
     else reinterpret_cast<uint4*>(v_pages + dst)[tid - 8] = vs[tid - 8];
   }
-  if (tid < kHd) s_q[tid] = __bfloat162float(qkv[my_row + h * kHd + tid]) * (0.125f * kLog2e);
-  __syncthreads();
 
   // rows of position j: cached pages for j < p0, this step's qkv rows otherwise (other blocks write those)
   auto k_row = [&](int j) -> const __nv_bfloat16* {
     if (j >= p0) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + d + h * kHd;
-    const int page = block_table[b * max_pages + j / page_size];
-    return k_pages + ((long long)page * page_size + j % page_size) * d + h * kHd;
+    return k_pages + ((long long)s_bt[j / page_size] * page_size + j % page_size) * d + h * kHd;
   };
   auto v_row = [&](int j) -> const __nv_bfloat16* {
     if (j >= p0) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + 2 * d + h * kHd;
-    const int page = block_table[b * max_pages + j / page_size];
-    return v_pages + ((long long)page * page_size + j % page_size) * d + h * kHd;
+    return v_pages + ((long long)s_bt[j / page_size] * page_size + j % page_size) * d + h * kHd;
   };
 
+  // scores: one key row (128 B = 8 x 16 B independent loads) per thread
   float mx = -INFINITY;
   for (int j = tid; j < n_keys; j += kSelfThreads) {
     const uint4* kr = reinterpret_cast<const uint4*>(k_row(j));
+    uint4 u[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) u[c] = kr[c];
     float acc = 0.0f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const uint4 u = kr[c];
-      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      const float2 a0 = unpack_bf16x2(u[c].x), a1 = unpack_bf16x2(u[c].y), a2 = unpack_bf16x2(u[c].z), a3 = unpack_bf16x2(u[c].w);
       acc = fmaf(a0.x, s_q[8 * c + 0], acc);
       acc = fmaf(a0.y, s_q[8 * c + 1], acc);
       acc = fmaf(a1.x, s_q[8 * c + 2], acc);
@@ -317,25 +320,39 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_q, in
   float sum = 0.0f;
   for (int j = tid; j < n_keys; j += kSelfThreads) {
     const float p = fast_exp2(s_p[j] - mx);
-    s_p[j] = p;
     sum += p;
+    s_p[j] = __bfloat162float(__float2bfloat16(p));  // bf16 probabilities, as in the tensor-core path
   }
   sum = warp_sum(sum);
   if (lane == 0) s_red[warp] = sum;
   __syncthreads();
   sum = s_red[0] + s_red[1] + s_red[2] + s_red[3];
 
-  // output: two groups of 64 threads split the keys, thread owns one of the 64 dims
-  const int g = tid >> 6, dim = tid & 63;
-  float acc = 0.0f;
-  for (int j = g; j < n_keys; j += 2) {
-    const float p = __bfloat162float(__float2bfloat16(s_p[j]));  // bf16 probabilities, as in the tensor-core path
-    acc = fmaf(p, __bfloat162float(v_row(j)[dim]), acc);
+  // output: warp w takes keys w, w+4, ...; a lane owns two of the 64 dims (one coalesced 128 B row per load),
+  // eight rows in flight per warp
+  float acc0 = 0.0f, acc1 = 0.0f;
+  for (int j0 = warp; j0 < n_keys; j0 += 4 * 8) {
+    uint32_t u[8];
+    float p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = j0 + 4 * i;
+      const bool ok = j < n_keys;
+      u[i] = ok ? reinterpret_cast<const uint32_t*>(v_row(j))[lane] : 0u;
+      p[i] = ok ? s_p[j] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 v = unpack_bf16x2(u[i]);
+      acc0 = fmaf(p[i], v.x, acc0);
+      acc1 = fmaf(p[i], v.y, acc1);
+    }
   }
-  s_acc[g][dim] = acc;
+  s_acc[warp][2 * lane] = acc0;
+  s_acc[warp][2 * lane + 1] = acc1;
   __syncthreads();
   if (tid < kHd) {
-    const float v = (s_acc[0][tid] + s_acc[1][tid]) / sum;
+    const float v = (s_acc[0][tid] + s_acc[1][tid] + s_acc[2][tid] + s_acc[3][tid]) / sum;
     out[((long long)b * n_q + qi) * d + h * kHd + tid] = __float2bfloat16(v);
   }
 }

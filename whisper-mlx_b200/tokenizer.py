@@ -111,10 +111,17 @@ class _Encoding:
     def decode(self, ids: List[int]) -> str:
         if self._tk is not None:
             return self._tk.decode(ids)
-        parts = []
-        for t in ids:
-            parts.append(self._special_by_id[t].encode() if t in self._special_by_id else _surrogate_piece(int(t)))
-        return b"".join(parts).decode("utf-8", errors="replace")
+        table = self._piece_table()
+        return b"".join(table[t] for t in ids).decode("utf-8", errors="replace")
+
+    def _piece_table(self) -> List[bytes]:
+        """id -> bytes for the surrogate vocabulary, built once (decode is on the per-window host path)."""
+        if getattr(self, "_table", None) is None:
+            n_base = min(self.special_tokens.values())
+            table = [_surrogate_piece(t) for t in range(n_base)]
+            table.extend(self._special_by_id[t].encode() for t in range(n_base, self.n_vocab))
+            self._table = table
+        return self._table
 
 
 @dataclass

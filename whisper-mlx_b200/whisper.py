@@ -85,7 +85,7 @@ class Whisper:
         def attn_fused(prefix, d):
             wq, wk, wv = w[prefix + ".query.weight"], w[prefix + ".key.weight"], w[prefix + ".value.weight"]
             bq, bv = w[prefix + ".query.bias"], w[prefix + ".value.bias"]
-            zero = torch.zeros(d, dtype=bq.dtype)
+            zero = torch.zeros(d, dtype=bq.dtype, device=bq.device)
             return (self._dev(torch.cat([wq, wk, wv], 0), bf), self._dev(torch.cat([bq.float(), zero.float(), bv.float()], 0), f32))
 
         d = dm.n_audio_state
