@@ -85,6 +85,14 @@ int b200w_mel_windows(const float* mel, const float* gmax, const long long* row0
 int b200w_gemm_bf16(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias,
                     const float* resid, int M, int N, int K, int flags, void* stream);
 
+/* Split-K form for decode steps (M <= 128 rows, one row tile): the K range is cut into
+ * b200w_gemm_splitk_slices(K, split_k) slices so that all SMs stream weights; slice s stores its raw fp32
+ * partial product to part + s * split_stride (rows of ldp floats).  No bias / activation: the consumer
+ * (b200w_residual_layernorm, b200w_decoder_*_attention_splitk) sums the slabs. */
+int b200w_gemm_bf16_splitk(const void* A, long long lda, const void* W, float* part, long long ldp, long long split_stride,
+                           int M, int N, int K, int split_k, void* stream);
+int b200w_gemm_splitk_slices(int K, int split_k);
+
 /* K2/K3  conv stem as implicit GEMM.  Replaces nn.Conv1d(k=3, padding=1, stride) + nn.gelu (+ positional
  * add) in UPSTREAM whisper.py::AudioEncoder.__call__.  x_padded: (B, T_in + 2, C_in) bf16 with zero first
  * and last rows; w: (C_out, 3 * C_in) bf16 = the MLX (out, k, in) layout flattened; out: (B * T_out, C_out)
@@ -96,6 +104,13 @@ int b200w_conv1d_gelu(const void* x_padded, const void* w, const float* bias, in
  * Replaces nn.LayerNorm in UPSTREAM whisper.py::ResidualAttentionBlock. */
 int b200w_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, void* out_bf16,
                     float* out_f32, void* stream);
+
+/* K4b decode-step residual update fused with the next LayerNorm (rows <= a few hundred, d % 128 == 0):
+ *   x <- x + bias + sum_{s < n_split} part[s]   (n_split == 0: x unchanged),   out <- LayerNorm(x) as bf16.
+ * Replaces `x = x + out_proj(...)` / `x = x + mlp2(...)` followed by the next nn.LayerNorm in UPSTREAM
+ * whisper.py::ResidualAttentionBlock for single-token decoder steps. */
+int b200w_residual_layernorm(float* x, const float* part, int n_split, long long split_stride, const float* bias,
+                             const float* gamma, const float* beta, int rows, int d, void* out_bf16, void* stream);
 
 /* K6  encoder self-attention (non-causal) on the fused (B*T, 3d) bf16 QKV activation -> (B*T, d) bf16.
  * Replaces UPSTREAM whisper.py::MultiHeadAttention.qkv_attention for the AudioEncoder. */
@@ -109,11 +124,22 @@ int b200w_decoder_self_attention(const void* qkv, int n_seq, int n_q, int n_head
                                  void* v_pages, const int* block_table, int max_pages, int page_size, void* out,
                                  void* stream);
 
+/* K7 with the fused QKV projection given as split-K partial slabs (rows of 3d floats, one new token per
+ * sequence): reduces q/k/v (+ bias_qkv), rounds to bf16, appends k/v to the pages, attends. */
+int b200w_decoder_self_attention_splitk(const float* qkv_part, int n_split, long long split_stride, const float* bias_qkv,
+                                        int n_seq, int n_head, const int* pos, void* k_pages, void* v_pages,
+                                        const int* block_table, int max_pages, int page_size, void* out, void* stream);
+
 /* K8  decoder cross-attention.  q: (n_seq * n_q, d) bf16; cross_kv: slots of (T, 2d) bf16 rows [K | V],
  * seq_stride elements apart; slot[b] names the slot of sequence b.  Replaces the cached-`xa` branch of
  * UPSTREAM whisper.py::MultiHeadAttention.__call__. */
 int b200w_decoder_cross_attention(const void* q, int n_seq, int n_q, int n_head, const void* cross_kv,
                                   long long seq_stride, int T, const int* slot, void* out, void* stream);
+
+/* K8 with the query projection given as split-K partial slabs (rows of d floats, one query per sequence). */
+int b200w_decoder_cross_attention_splitk(const float* q_part, int n_split, long long split_stride, const float* bias_q,
+                                         int n_seq, int n_head, const void* cross_kv, long long seq_stride, int T,
+                                         const int* slot, void* out, void* stream);
 
 /* K10 token + positional embedding: x[b*n_q+qi] = tok_emb[tokens[b][pos[b]+qi]] + pos_emb[pos[b]+qi] (f32). */
 int b200w_embed(const int* tokens, int tokens_ld, const int* pos, int n_seq, int n_q, const void* tok_emb,

@@ -341,6 +341,78 @@ def case_decoder_attention():
     return out
 
 
+def case_splitk_decode_ops():
+    """Split-K decode GEMM + the consumers that fold the partial slabs (residual+LN, self / cross attention)."""
+    L, lib = _lib()
+    out = {}
+    g = torch.Generator().manual_seed(0)
+    H, d, ps, M = 6, 384, 16, 120
+    # ---- GEMM partial slabs sum to the product
+    for (N, K, split) in ((384, 384, 3), (1280, 1280, 7), (1280, 5120, 7), (3840, 1280, 2), (384, 1536, 8)):
+        a = _bf16(torch.randn(M, K, generator=g)).cuda()
+        w = _bf16(torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+        n_sl = lib.b200w_gemm_splitk_slices(K, split)
+        part = torch.full((n_sl, 128, N), float("nan"), dtype=torch.float32, device="cuda")
+        L.check(lib.b200w_gemm_bf16_splitk(L.ptr(a), K, L.ptr(w), L.ptr(part), N, 128 * N, M, N, K, split, L.stream()))
+        torch.cuda.synchronize()
+        ref = a.float() @ w.float().T
+        err = (part[:, :M].sum(0) - ref).abs().max().item()
+        out[f"gemm_{N}x{K}s{n_sl}"] = err
+        assert err <= 2e-3 * max(1.0, ref.abs().max().item()), (N, K, err)
+    # ---- residual + LayerNorm
+    n_sl = 5
+    x = torch.randn(M, d, generator=g).cuda()
+    part = (torch.randn(n_sl, 128, d, generator=g) * 0.3).cuda()
+    bias, gm, bt = torch.randn(d, generator=g).cuda(), torch.randn(d, generator=g).cuda(), torch.randn(d, generator=g).cuda()
+    x_ref = x + bias + part[:, :M].sum(0)
+    h_ref = torch.nn.functional.layer_norm(x_ref, (d,), gm, bt, eps=1e-5)
+    xo = x.clone()
+    h = torch.empty((M, d), dtype=torch.bfloat16, device="cuda")
+    L.check(lib.b200w_residual_layernorm(L.ptr(xo), L.ptr(part), n_sl, 128 * d, L.ptr(bias), L.ptr(gm), L.ptr(bt), M, d, L.ptr(h), L.stream()))
+    torch.cuda.synchronize()
+    out["resid_x"] = (xo - x_ref).abs().max().item()
+    out["resid_ln"] = (h.float() - h_ref).abs().max().item()
+    assert out["resid_x"] <= 1e-5 and out["resid_ln"] <= 2 ** -7 * max(1.0, h_ref.abs().max().item())
+    x2 = x.clone()
+    L.check(lib.b200w_residual_layernorm(L.ptr(x2), None, 0, 0, None, L.ptr(gm), L.ptr(bt), M, d, L.ptr(h), L.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(x2, x)
+    assert (h.float() - torch.nn.functional.layer_norm(x, (d,), gm, bt, eps=1e-5)).abs().max().item() <= 2 ** -7 * 8
+    # ---- attention consumers: partial slabs + bias must behave exactly like the bf16 activation they sum to
+    B, max_pages, n_sl = 5, 8, 3
+    pos = torch.tensor([0, 5, 37, 16, 100], dtype=torch.int32).cuda()
+    bt_tab = torch.randperm(B * max_pages, generator=g).to(torch.int32).view(B, max_pages).contiguous().cuda()
+    kp = _bf16(torch.randn(B * max_pages, ps, d, generator=g)).cuda()
+    vp = _bf16(torch.randn(B * max_pages, ps, d, generator=g)).cuda()
+    bias3 = torch.randn(3 * d, generator=g).cuda()
+    part3 = torch.randn(n_sl, 128, 3 * d, generator=g).cuda()
+    qkv = _bf16(part3[:, :B].sum(0) + bias3).view(B, 1, 3 * d).contiguous()
+    o_ref = torch.empty((B, 1, d), dtype=torch.bfloat16, device="cuda")
+    o_got = torch.empty_like(o_ref)
+    kp1, vp1, kp2, vp2 = kp.clone(), vp.clone(), kp.clone(), vp.clone()
+    L.check(lib.b200w_decoder_self_attention(L.ptr(qkv), B, 1, H, L.ptr(pos), L.ptr(kp1), L.ptr(vp1), L.ptr(bt_tab), max_pages,
+                                             ps, L.ptr(o_ref), L.stream()))
+    L.check(lib.b200w_decoder_self_attention_splitk(L.ptr(part3), n_sl, 128 * 3 * d, L.ptr(bias3), B, H, L.ptr(pos), L.ptr(kp2),
+                                                    L.ptr(vp2), L.ptr(bt_tab), max_pages, ps, L.ptr(o_got), L.stream()))
+    torch.cuda.synchronize()
+    out["self_splitk"] = (o_got.float() - o_ref.float()).abs().max().item()
+    assert torch.equal(kp1, kp2) and torch.equal(vp1, vp2), "appended K/V rows differ"
+    assert out["self_splitk"] <= 1e-2
+    T, n_slots = 1500, 3
+    slot = torch.tensor([2, 0, 1, 1, 0], dtype=torch.int32).cuda()
+    ckv = _bf16(torch.randn(n_slots, T, 2 * d, generator=g)).cuda()
+    bias1 = torch.randn(d, generator=g).cuda()
+    part1 = torch.randn(n_sl, 128, d, generator=g).cuda()
+    q = _bf16(part1[:, :B].sum(0) + bias1).view(B, 1, d).contiguous()
+    L.check(lib.b200w_decoder_cross_attention(L.ptr(q), B, 1, H, L.ptr(ckv), T * 2 * d, T, L.ptr(slot), L.ptr(o_ref), L.stream()))
+    L.check(lib.b200w_decoder_cross_attention_splitk(L.ptr(part1), n_sl, 128 * d, L.ptr(bias1), B, H, L.ptr(ckv), T * 2 * d, T,
+                                                     L.ptr(slot), L.ptr(o_got), L.stream()))
+    torch.cuda.synchronize()
+    out["cross_splitk"] = (o_got.float() - o_ref.float()).abs().max().item()
+    assert out["cross_splitk"] <= 1e-2
+    return out
+
+
 # ------------------------------------------------------------------------------------------ K9
 def case_filter_argmax():
     """Every branch of the suppression / timestamp grammar against the oracle's host-side rules."""
@@ -555,6 +627,7 @@ CASES = {
     "layernorm_embed": case_layernorm_embed,
     "encoder_attention": case_encoder_attention,
     "decoder_attention": case_decoder_attention,
+    "splitk_decode_ops": case_splitk_decode_ops,
     "filter_argmax": case_filter_argmax,
     "encoder_tiny": case_encoder_tiny,
     "decoder_tiny": case_decoder_tiny,

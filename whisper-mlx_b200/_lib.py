@@ -74,6 +74,11 @@ SIGNATURES = {
     "b200w_logmel_finalize": (i32, [vp, vp, i32, i64, vp]),
     "b200w_mel_windows": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp]),
     "b200w_gemm_bf16": (i32, [vp, i64, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp]),
+    "b200w_gemm_bf16_splitk": (i32, [vp, i64, vp, vp, i64, i64, i32, i32, i32, i32, vp]),
+    "b200w_gemm_splitk_slices": (i32, [i32, i32]),
+    "b200w_residual_layernorm": (i32, [vp, vp, i32, i64, vp, vp, vp, i32, i32, vp, vp]),
+    "b200w_decoder_self_attention_splitk": (i32, [vp, i32, i64, vp, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp]),
+    "b200w_decoder_cross_attention_splitk": (i32, [vp, i32, i64, vp, i32, i32, vp, i64, i32, vp, vp, vp]),
     "b200w_conv1d_gelu": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, i64, i32, vp]),
     "b200w_layernorm": (i32, [vp, vp, vp, i32, i32, vp, vp, vp]),
     "b200w_encoder_attention": (i32, [vp, i32, i32, i32, vp, vp]),

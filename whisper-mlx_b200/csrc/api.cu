@@ -111,6 +111,40 @@ static int gemm(const void* A, long long lda, int M, const void* W, int N, int K
   return launch_gemm(ta, tb, p, bn, stream);
 }
 
+// Split-K plan for a single-row-tile (decode) GEMM: enough K slices that ~all SMs stream weights, each slice
+// at least two K blocks.  Per-SM TMA ingest (~85 GB/s measured) times the per-CTA bytes is what bounds these
+// launches, so the work is spread over as many CTAs as fit in one wave.
+static int plan_split_k(int N, int K, int bn) {
+  const int tiles = ceil_div(N, bn), num_kb = ceil_div(K, 64);
+  int s = device_sm_count() / tiles;
+  if (s > 8) s = 8;
+  if (s > num_kb / 2) s = num_kb / 2;
+  if (s < 1) s = 1;
+  const int kb_per = ceil_div(num_kb, s);
+  return ceil_div(num_kb, kb_per);
+}
+
+// part[s] (M, ldp) f32 = A(:, K-slice s) W(:, K-slice s)^T for s < split (the consumer kernel sums the slabs)
+static int gemm_splitk(const void* A, long long lda, int M, const void* W, int N, int K, float* part, long long ldp,
+                       long long split_stride, int split, int bn, cudaStream_t stream) {
+  B200W_CHECK_ARG(M > 0 && M <= 128 && split >= 1, "gemm_splitk: needs a single row tile (M=%d)", M);
+  GemmParams p{};
+  p.n_batch = 1;
+  p.rows_per_batch = M;
+  p.N = N;
+  p.K = K;
+  p.n_store = N;
+  p.out = part;
+  p.ldc = ldp;
+  p.out_f32 = 1;
+  p.split_k = split;
+  p.split_stride = split_stride;
+  CUtensorMap ta, tb;
+  B200W_TRY(make_tmap_a(&ta, A, 1, M, K, lda, (long long)M * lda));
+  B200W_TRY(make_tmap_w(&tb, W, N, K, bn));
+  return launch_gemm(ta, tb, p, bn, stream);
+}
+
 static int conv1d_gelu(const void* x_padded, const void* w, const float* bias, int n_batch, int t_in, int c_in,
                        int c_out, int stride, const float* pos, void* out, long long out_ld, bool out_f32,
                        cudaStream_t stream) {
@@ -178,7 +212,9 @@ static size_t carve_encoder(const b200w_dims& dm, int B, Carver& c, EncBufs* o) 
 
 struct DecBufs {
   void *x, *h, *qkv, *att, *qc, *mlp;
+  float *part_qkv, *part_q, *part_res;  // split-K partial slabs (decode steps with <= 128 rows)
 };
+constexpr int kMaxSplit = 8;
 static size_t carve_decoder(const b200w_dims& dm, int n_seq, int n_q, Carver& c, DecBufs* o) {
   const size_t d = dm.n_text_state;
   const size_t rows = align_up((size_t)n_seq * n_q, 128);  // TMA boxes may read (zero-filled) past M, never past the buffer
@@ -188,7 +224,13 @@ static size_t carve_decoder(const b200w_dims& dm, int n_seq, int n_q, Carver& c,
   void* att = c.take(rows * d * 2);
   void* qc = c.take(rows * d * 2);
   void* mlp = c.take(rows * 4 * d * 2);
-  if (o) *o = DecBufs{x, h, qkv, att, qc, mlp};
+  float *pq = nullptr, *p1 = nullptr, *pr = nullptr;
+  if (rows <= 128) {
+    pq = static_cast<float*>(c.take((size_t)kMaxSplit * 128 * 3 * d * 4));
+    p1 = static_cast<float*>(c.take((size_t)kMaxSplit * 128 * d * 4));
+    pr = static_cast<float*>(c.take((size_t)kMaxSplit * 128 * d * 4));
+  }
+  if (o) *o = DecBufs{x, h, qkv, att, qc, mlp, pq, p1, pr};
   return c.off;
 }
 
@@ -265,6 +307,43 @@ int b200w_decoder_cross_attention(const void* q, int n_seq, int n_q, int n_head,
   B200W_CHECK_ARG(q && cross_kv && slot && out, "cross_attention: null pointer");
   return launch_decoder_cross_attention((const __nv_bfloat16*)q, n_seq, n_q, n_head, (const __nv_bfloat16*)cross_kv,
                                         seq_stride, T, slot, (__nv_bfloat16*)out, (cudaStream_t)stream);
+}
+
+int b200w_gemm_bf16_splitk(const void* A, long long lda, const void* W, float* part, long long ldp, long long split_stride,
+                           int M, int N, int K, int split_k, void* stream) {
+  B200W_CHECK_ARG(A && W && part && split_k >= 1 && split_k <= kMaxSplit, "gemm_splitk: bad arguments");
+  return gemm_splitk(A, lda, M, W, N, K, part, ldp, split_stride, split_k, 64, (cudaStream_t)stream);
+}
+
+int b200w_gemm_splitk_slices(int K, int split_k) {
+  const int num_kb = ceil_div(K, 64);
+  if (split_k < 1) split_k = 1;
+  return ceil_div(num_kb, ceil_div(num_kb, split_k));
+}
+
+int b200w_residual_layernorm(float* x, const float* part, int n_split, long long split_stride, const float* bias,
+                             const float* gamma, const float* beta, int rows, int d, void* out_bf16, void* stream) {
+  B200W_CHECK_ARG(x && gamma && beta && out_bf16, "residual_layernorm: null pointer");
+  return launch_resid_ln_small(x, part, n_split, split_stride, bias, gamma, beta, rows, d, (__nv_bfloat16*)out_bf16,
+                               (cudaStream_t)stream);
+}
+
+int b200w_decoder_self_attention_splitk(const float* qkv_part, int n_split, long long split_stride, const float* bias_qkv,
+                                        int n_seq, int n_head, const int* pos, void* k_pages, void* v_pages,
+                                        const int* block_table, int max_pages, int page_size, void* out, void* stream) {
+  B200W_CHECK_ARG(qkv_part && bias_qkv && pos && k_pages && v_pages && block_table && out && n_split >= 1,
+                  "self_attention_splitk: bad arguments");
+  return launch_decoder_self_attention(nullptr, n_seq, 1, n_head, pos, (__nv_bfloat16*)k_pages, (__nv_bfloat16*)v_pages,
+                                       block_table, max_pages, page_size, (__nv_bfloat16*)out, (cudaStream_t)stream,
+                                       qkv_part, n_split, split_stride, bias_qkv);
+}
+
+int b200w_decoder_cross_attention_splitk(const float* q_part, int n_split, long long split_stride, const float* bias_q,
+                                         int n_seq, int n_head, const void* cross_kv, long long seq_stride, int T,
+                                         const int* slot, void* out, void* stream) {
+  B200W_CHECK_ARG(q_part && bias_q && cross_kv && slot && out && n_split >= 1, "cross_attention_splitk: bad arguments");
+  return launch_decoder_cross_attention(nullptr, n_seq, 1, n_head, (const __nv_bfloat16*)cross_kv, seq_stride, T, slot,
+                                        (__nv_bfloat16*)out, (cudaStream_t)stream, q_part, n_split, split_stride, bias_q);
 }
 
 int b200w_embed(const int* tokens, int tokens_ld, const int* pos, int n_seq, int n_q, const void* tok_emb,
@@ -428,26 +507,62 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   float* x = static_cast<float*>(bf.x);
   B200W_TRY(launch_embed(st->tokens, st->tokens_ld, st->pos, B, n_q, (const __nv_bfloat16*)m.w.tok_emb,
                          (const __nv_bfloat16*)m.w.dec_pos, d, dm.n_text_ctx, x, stream));
-  for (int l = 0; l < dm.n_text_layer; ++l) {
-    const b200w_dec_layer& L = m.dec[l];
-    __nv_bfloat16* kp = static_cast<__nv_bfloat16*>(st->k_pages) + (size_t)l * st->layer_page_stride;
-    __nv_bfloat16* vp = static_cast<__nv_bfloat16*>(st->v_pages) + (size_t)l * st->layer_page_stride;
-    const __nv_bfloat16* ckv = static_cast<const __nv_bfloat16*>(st->cross_kv) + (size_t)l * st->cross_layer_stride;
-    B200W_TRY(launch_layernorm(x, L.attn_ln_g, L.attn_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
-    B200W_TRY(gemm(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.qkv, 3 * d, false, L.b_qkv, false, nullptr, 0, 0, stream));
-    B200W_TRY(launch_decoder_self_attention((const __nv_bfloat16*)bf.qkv, B, n_q, H, st->pos, kp, vp, st->block_table,
-                                            st->max_pages, st->page_size, (__nv_bfloat16*)bf.att, stream));
-    B200W_TRY(gemm(bf.att, d, rows, L.w_out, d, d, x, d, true, L.b_out, false, x, d, 0, stream));
-    B200W_TRY(launch_layernorm(x, L.cross_ln_g, L.cross_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
-    B200W_TRY(gemm(bf.h, d, rows, L.w_cq, d, d, bf.qc, d, false, L.b_cq, false, nullptr, 0, 0, stream));
-    B200W_TRY(launch_decoder_cross_attention((const __nv_bfloat16*)bf.qc, B, n_q, H, ckv, (long long)T * 2 * d, T,
-                                             st->cross_slot, (__nv_bfloat16*)bf.att, stream));
-    B200W_TRY(gemm(bf.att, d, rows, L.w_cout, d, d, x, d, true, L.b_cout, false, x, d, 0, stream));
-    B200W_TRY(launch_layernorm(x, L.mlp_ln_g, L.mlp_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
-    B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));
-    B200W_TRY(gemm(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, x, d, true, L.b_mlp2, false, x, d, 0, stream));
+  const bool small = rows <= 128 && n_q == 1;  // decode steps: split-K GEMMs whose reduction is fused into the consumers
+  if (small) {
+    const int bn = 64;
+    const long long s3 = 128ll * 3 * d, s1 = 128ll * d;
+    const int sp_qkv = plan_split_k(3 * d, d, bn), sp_d = plan_split_k(d, d, bn), sp_mlp2 = plan_split_k(d, 4 * d, bn);
+    int pend = 0;  // split count of the residual GEMM whose partials (+ bias) the next LayerNorm folds into x
+    const float* pend_bias = nullptr;
+    for (int l = 0; l < dm.n_text_layer; ++l) {
+      const b200w_dec_layer& L = m.dec[l];
+      __nv_bfloat16* kp = static_cast<__nv_bfloat16*>(st->k_pages) + (size_t)l * st->layer_page_stride;
+      __nv_bfloat16* vp = static_cast<__nv_bfloat16*>(st->v_pages) + (size_t)l * st->layer_page_stride;
+      const __nv_bfloat16* ckv = static_cast<const __nv_bfloat16*>(st->cross_kv) + (size_t)l * st->cross_layer_stride;
+      B200W_TRY(launch_resid_ln_small(x, bf.part_res, pend, s1, pend_bias, L.attn_ln_g, L.attn_ln_b, rows, d,
+                                      (__nv_bfloat16*)bf.h, stream));
+      B200W_TRY(gemm_splitk(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.part_qkv, 3 * d, s3, sp_qkv, bn, stream));
+      B200W_TRY(launch_decoder_self_attention(nullptr, B, 1, H, st->pos, kp, vp, st->block_table, st->max_pages,
+                                              st->page_size, (__nv_bfloat16*)bf.att, stream, bf.part_qkv, sp_qkv, s3,
+                                              L.b_qkv));
+      B200W_TRY(gemm_splitk(bf.att, d, rows, L.w_out, d, d, bf.part_res, d, s1, sp_d, bn, stream));
+      B200W_TRY(launch_resid_ln_small(x, bf.part_res, sp_d, s1, L.b_out, L.cross_ln_g, L.cross_ln_b, rows, d,
+                                      (__nv_bfloat16*)bf.h, stream));
+      B200W_TRY(gemm_splitk(bf.h, d, rows, L.w_cq, d, d, bf.part_q, d, s1, sp_d, bn, stream));
+      B200W_TRY(launch_decoder_cross_attention(nullptr, B, 1, H, ckv, (long long)T * 2 * d, T, st->cross_slot,
+                                               (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq));
+      B200W_TRY(gemm_splitk(bf.att, d, rows, L.w_cout, d, d, bf.part_res, d, s1, sp_d, bn, stream));
+      B200W_TRY(launch_resid_ln_small(x, bf.part_res, sp_d, s1, L.b_cout, L.mlp_ln_g, L.mlp_ln_b, rows, d,
+                                      (__nv_bfloat16*)bf.h, stream));
+      B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));
+      B200W_TRY(gemm_splitk(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, bf.part_res, d, s1, sp_mlp2, bn, stream));
+      pend = sp_mlp2;
+      pend_bias = L.b_mlp2;
+    }
+    B200W_TRY(launch_resid_ln_small(x, bf.part_res, pend, s1, pend_bias, m.w.dec_ln_g, m.w.dec_ln_b, rows, d,
+                                    (__nv_bfloat16*)bf.h, stream));
+  } else {
+    for (int l = 0; l < dm.n_text_layer; ++l) {
+      const b200w_dec_layer& L = m.dec[l];
+      __nv_bfloat16* kp = static_cast<__nv_bfloat16*>(st->k_pages) + (size_t)l * st->layer_page_stride;
+      __nv_bfloat16* vp = static_cast<__nv_bfloat16*>(st->v_pages) + (size_t)l * st->layer_page_stride;
+      const __nv_bfloat16* ckv = static_cast<const __nv_bfloat16*>(st->cross_kv) + (size_t)l * st->cross_layer_stride;
+      B200W_TRY(launch_layernorm(x, L.attn_ln_g, L.attn_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+      B200W_TRY(gemm(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.qkv, 3 * d, false, L.b_qkv, false, nullptr, 0, 0, stream));
+      B200W_TRY(launch_decoder_self_attention((const __nv_bfloat16*)bf.qkv, B, n_q, H, st->pos, kp, vp, st->block_table,
+                                              st->max_pages, st->page_size, (__nv_bfloat16*)bf.att, stream));
+      B200W_TRY(gemm(bf.att, d, rows, L.w_out, d, d, x, d, true, L.b_out, false, x, d, 0, stream));
+      B200W_TRY(launch_layernorm(x, L.cross_ln_g, L.cross_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+      B200W_TRY(gemm(bf.h, d, rows, L.w_cq, d, d, bf.qc, d, false, L.b_cq, false, nullptr, 0, 0, stream));
+      B200W_TRY(launch_decoder_cross_attention((const __nv_bfloat16*)bf.qc, B, n_q, H, ckv, (long long)T * 2 * d, T,
+                                               st->cross_slot, (__nv_bfloat16*)bf.att, stream));
+      B200W_TRY(gemm(bf.att, d, rows, L.w_cout, d, d, x, d, true, L.b_cout, false, x, d, 0, stream));
+      B200W_TRY(launch_layernorm(x, L.mlp_ln_g, L.mlp_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+      B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));
+      B200W_TRY(gemm(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, x, d, true, L.b_mlp2, false, x, d, 0, stream));
+    }
+    B200W_TRY(launch_layernorm(x, m.w.dec_ln_g, m.w.dec_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
   }
-  B200W_TRY(launch_layernorm(x, m.w.dec_ln_g, m.w.dec_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
   // tied logits, last new token of every sequence: a strided view of h (row stride n_q * d)
   const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(bf.h);
   {

@@ -247,11 +247,16 @@ int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n
 constexpr int kSelfThreads = 128;
 constexpr int kMaxSelfKeys = 448;
 
+__device__ __forceinline__ int s_bt_or(const int* block_table, int b, int max_pages, int j, int page_size) {
+  return block_table[b * max_pages + j / page_size];
+}
+
 __global__ void __launch_bounds__(kSelfThreads)
 decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_q, int n_head, const int* __restrict__ pos,
                               __nv_bfloat16* __restrict__ k_pages, __nv_bfloat16* __restrict__ v_pages,
                               const int* __restrict__ block_table, int max_pages, int page_size,
-                              __nv_bfloat16* __restrict__ out) {
+                              __nv_bfloat16* __restrict__ out, const float* __restrict__ part, int n_split,
+                              long long split_stride, const float* __restrict__ bias) {
   __shared__ float s_q[kHd];
   __shared__ float s_p[kMaxSelfKeys];
   __shared__ float s_red[kSelfThreads / 32];
@@ -266,11 +271,29 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_q, in
   const long long my_row = ((long long)b * n_q + qi) * 3 * d;
 
   if (tid < max_pages) s_bt[tid] = block_table[b * max_pages + tid];
-  if (tid >= 64) s_q[tid - 64] = __bfloat162float(qkv[my_row + h * kHd + tid - 64]) * (0.125f * kLog2e);
+  const bool split_mode = n_split > 0;  // qkv arrives as split-K fp32 partial slabs (+ bias), n_q == 1
+  if (split_mode) {
+    // reduce the partials of this head's q / k / v slices, round to bf16 like the GEMM epilogue would have
+    for (int e = tid; e < 3 * kHd; e += kSelfThreads) {
+      const int which = e / kHd, t = e - which * kHd;
+      const long long col = (long long)which * d + h * kHd + t;
+      float v = bias[col];
+      for (int sidx = 0; sidx < n_split; ++sidx) v += part[sidx * split_stride + (long long)b * 3 * d + col];
+      const __nv_bfloat16 vb = __float2bfloat16(v);
+      if (which == 0) {
+        s_q[t] = __bfloat162float(vb) * (0.125f * kLog2e);
+      } else {
+        const long long dst = ((long long)s_bt_or(block_table, b, max_pages, p0, page_size) * page_size + p0 % page_size) * d + h * kHd + t;
+        (which == 1 ? k_pages : v_pages)[dst] = vb;
+      }
+    }
+  } else if (tid >= 64) {
+    s_q[tid - 64] = __bfloat162float(qkv[my_row + h * kHd + tid - 64]) * (0.125f * kLog2e);
+  }
   __syncthreads();
 
   // append this token's k / v rows to the paged cache (each (b, h, qi) block owns its 64-wide slice)
-  if (tid < 16) {
+  if (!split_mode && tid < 16) {
     const int j = p0 + qi;
     const long long dst = ((long long)s_bt[j / page_size] * page_size + j % page_size) * d + h * kHd;
     const uint4* ks = reinterpret_cast<const uint4*>(qkv + my_row + d + h * kHd);
@@ -281,11 +304,11 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_q, in
 
   // rows of position j: cached pages for j < p0, this step's qkv rows otherwise (other blocks write those)
   auto k_row = [&](int j) -> const __nv_bfloat16* {
-    if (j >= p0) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + d + h * kHd;
+    if (j >= p0 && !split_mode) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + d + h * kHd;
     return k_pages + ((long long)s_bt[j / page_size] * page_size + j % page_size) * d + h * kHd;
   };
   auto v_row = [&](int j) -> const __nv_bfloat16* {
-    if (j >= p0) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + 2 * d + h * kHd;
+    if (j >= p0 && !split_mode) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + 2 * d + h * kHd;
     return v_pages + ((long long)s_bt[j / page_size] * page_size + j % page_size) * d + h * kHd;
   };
 
@@ -359,12 +382,16 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_q, in
 
 int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, int n_head, const int* pos,
                                   __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, const int* block_table,
-                                  int max_pages_per_seq, int page_size, __nv_bfloat16* out, cudaStream_t stream) {
+                                  int max_pages_per_seq, int page_size, __nv_bfloat16* out, cudaStream_t stream,
+                                  const float* part, int n_split, long long split_stride, const float* bias) {
+  B200W_CHECK_ARG(n_split == 0 || (n_q == 1 && part && bias), "self_attention: split-K input needs n_q == 1");
+  B200W_CHECK_ARG(n_split > 0 || qkv, "self_attention: null qkv");
   B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "self_attention: bad sizes");
   B200W_CHECK_ARG(max_pages_per_seq * page_size <= kMaxSelfKeys, "self_attention: context above %d", kMaxSelfKeys);
   dim3 grid(n_head, n_seq, n_q);
   decoder_self_attention_kernel<<<grid, kSelfThreads, 0, stream>>>(qkv, n_q, n_head, pos, k_pages, v_pages,
-                                                                   block_table, max_pages_per_seq, page_size, out);
+                                                                   block_table, max_pages_per_seq, page_size, out,
+                                                                   part, n_split, split_stride, bias);
   B200W_LAUNCH_OK();
   count_launch();
   return kOk;
@@ -378,7 +405,9 @@ constexpr int kMaxCrossKeys = 1536;
 __global__ void __launch_bounds__(kCrossThreads)
 decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int n_head,
                                const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride, int T,
-                               const int* __restrict__ slot, __nv_bfloat16* __restrict__ out) {
+                               const int* __restrict__ slot, __nv_bfloat16* __restrict__ out,
+                               const float* __restrict__ part, int n_split, long long split_stride,
+                               const float* __restrict__ bias) {
   __shared__ float s_p[kMaxCrossKeys];
   __shared__ float s_red[kCrossWarps];
   __shared__ float s_part[kCrossWarps][kHd];
@@ -393,7 +422,21 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   const __nv_bfloat16* vbase = kbase + d;
 
   float qv[8];
-  {
+  if (n_split > 0) {
+    // q arrives as split-K fp32 partial slabs of the query projection (+ bias): reduce, round to bf16
+    const long long col = ((long long)b * n_q + qi) * d + h * kHd + sub * 8;
+    const float c = 0.125f * kLog2e;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = bias[h * kHd + sub * 8 + i];
+    for (int sidx = 0; sidx < n_split; ++sidx) {
+      const float4 a = *reinterpret_cast<const float4*>(part + sidx * split_stride + col);
+      const float4 e = *reinterpret_cast<const float4*>(part + sidx * split_stride + col + 4);
+      qv[0] += a.x; qv[1] += a.y; qv[2] += a.z; qv[3] += a.w;
+      qv[4] += e.x; qv[5] += e.y; qv[6] += e.z; qv[7] += e.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = __bfloat162float(__float2bfloat16(qv[i])) * c;
+  } else {
     const uint4 u = *reinterpret_cast<const uint4*>(q + ((long long)b * n_q + qi) * d + h * kHd + sub * 8);
     const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
     const float c = 0.125f * kLog2e;
@@ -500,12 +543,14 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
 
 int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, int n_head,
                                    const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
-                                   __nv_bfloat16* out, cudaStream_t stream) {
+                                   __nv_bfloat16* out, cudaStream_t stream, const float* part, int n_split,
+                                   long long split_stride, const float* bias) {
   B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "cross_attention: bad sizes");
+  B200W_CHECK_ARG(n_split > 0 ? (part && bias) : (q != nullptr), "cross_attention: missing query input");
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
   dim3 grid(n_head, n_seq, n_q);
   decoder_cross_attention_kernel<<<grid, kCrossThreads, 0, stream>>>(q, n_q, n_head, cross_kv, seq_stride, T, slot,
-                                                                     out);
+                                                                     out, part, n_split, split_stride, bias);
   B200W_LAUNCH_OK();
   count_launch();
   return kOk;

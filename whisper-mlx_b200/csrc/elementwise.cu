@@ -68,6 +68,56 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, int 
   return kOk;
 }
 
+// K4b: residual update + LayerNorm for the decode step (few rows): one CTA per row, one float4 per thread.
+//   x <- x + bias + sum_s part[s]   (the split-K partial slabs of the preceding residual GEMM)
+//   h <- LayerNorm(x) as bf16
+// Fuses the split-K reduction, the bias, the residual add and the next sub-layer's LayerNorm in one launch.
+__global__ void __launch_bounds__(320)
+resid_ln_small_kernel(float* __restrict__ x, const float* __restrict__ part, int n_split, long long split_stride,
+                      const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      int d, __nv_bfloat16* __restrict__ out_bf16) {
+  __shared__ float s_red[2][10];
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const long long off = (long long)row * d + tid * 4;
+  float4 v = *reinterpret_cast<const float4*>(x + off);
+  if (n_split > 0) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + tid);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    for (int s = 0; s < n_split; ++s) {
+      const float4 p = *reinterpret_cast<const float4*>(part + s * split_stride + off);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    *reinterpret_cast<float4*>(x + off) = v;
+  }
+  float sum = warp_sum((v.x + v.y) + (v.z + v.w));
+  if (lane == 0) s_red[0][warp] = sum;
+  __syncthreads();
+  sum = 0.0f;
+  for (int i = 0; i < nwarp; ++i) sum += s_red[0][i];
+  const float mean = sum / (float)d;
+  const float a = v.x - mean, b2 = v.y - mean, c = v.z - mean, e = v.w - mean;
+  float var = warp_sum((a * a + b2 * b2) + (c * c + e * e));
+  if (lane == 0) s_red[1][warp] = var;
+  __syncthreads();
+  var = 0.0f;
+  for (int i = 0; i < nwarp; ++i) var += s_red[1][i];
+  const float rstd = rsqrtf(var / (float)d + 1e-5f);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + tid), bb = __ldg(reinterpret_cast<const float4*>(beta) + tid);
+  *reinterpret_cast<uint2*>(out_bf16 + off) =
+      make_uint2(pack_bf16x2(a * rstd * g.x + bb.x, b2 * rstd * g.y + bb.y), pack_bf16x2(c * rstd * g.z + bb.z, e * rstd * g.w + bb.w));
+}
+
+int launch_resid_ln_small(float* x, const float* part, int n_split, long long split_stride, const float* bias,
+                          const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
+                          cudaStream_t stream) {
+  B200W_CHECK_ARG(rows > 0 && d % 128 == 0 && d <= 1280, "resid_ln: unsupported d=%d", d);
+  B200W_CHECK_ARG(n_split == 0 || (part != nullptr && bias != nullptr), "resid_ln: partials without bias");
+  resid_ln_small_kernel<<<rows, d / 4, 0, stream>>>(x, part, n_split, split_stride, bias, gamma, beta, d, out_bf16);
+  B200W_LAUNCH_OK();
+  count_launch();
+  return kOk;
+}
+
 // =============================================================================================== K10
 __global__ void embed_kernel(const int* __restrict__ tokens, int tokens_ld, const int* __restrict__ pos, int n_q,
                              const __nv_bfloat16* __restrict__ tok_emb, const __nv_bfloat16* __restrict__ pos_emb,

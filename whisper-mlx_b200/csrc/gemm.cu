@@ -54,7 +54,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   const int tiles_m = p.n_batch * p.tiles_m_per_batch;
-  const int num_tiles = tiles_m * p.tiles_n;
+  const int num_tiles = tiles_m * p.tiles_n * p.split_k;
   const int num_kb = (p.K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
@@ -81,7 +81,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   // tile id -> (m tile, n tile): groups of group_m row tiles sweep all n tiles so the A rows of a group
   // stay L2-resident while W (small) is re-read from L2.
-  auto decode_tile = [&](int id, int& mt, int& nt) {
+  // split-K: the K range of one (m, n) tile is cut into split_k slices handled by consecutive tile ids; each
+  // slice stores its raw fp32 partial to its own slab and the consumer kernel sums the slabs.
+  auto decode_tile = [&](int id, int& mt, int& nt, int& ks) {
+    ks = id % p.split_k;
+    id /= p.split_k;
     const int per_group = p.group_m * p.tiles_n;
     const int g = id / per_group;
     const int first_m = g * p.group_m;
@@ -96,12 +100,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int mt, nt;
-        decode_tile(tile, mt, nt);
+        int mt, nt, ks;
+        decode_tile(tile, mt, nt, ks);
         const int b = mt / p.tiles_m_per_batch;
         const int t0 = (mt - b * p.tiles_m_per_batch) * kBM;
         const int n0 = nt * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_end = min(num_kb, (ks + 1) * p.kb_per_split);
+        for (int kb = ks * p.kb_per_split; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           unsigned char* sa = smem + stage * Cfg::kStageBytes;
           unsigned char* sb = sa + Cfg::kABytes;
@@ -127,7 +132,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_begin = (tile % p.split_k) * p.kb_per_split;
+        const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -136,7 +143,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // +32 bytes along the swizzled row per K=16 slice -> +2 in the (addr >> 4) field
-            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb_begin || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
@@ -155,8 +162,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int mt, nt;
-      decode_tile(tile, mt, nt);
+      int mt, nt, ks;
+      decode_tile(tile, mt, nt, ks);
       const int b = mt / p.tiles_m_per_batch;
       const int t = (mt - b * p.tiles_m_per_batch) * kBM + q * 32 + lane;
       const bool row_ok = t < p.rows_per_batch;
@@ -205,7 +212,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
           }
           if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldc + col);
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ks * p.split_stride + orow * p.ldc + col);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
@@ -253,7 +260,16 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, GemmPara
   if (p.out_batch_rows <= 0) p.out_batch_rows = p.rows_per_batch;
   p.tiles_m_per_batch = ceil_div(p.rows_per_batch, kBM);
   p.tiles_n = ceil_div(p.n_store, BN);
-  const long long tiles = (long long)p.n_batch * p.tiles_m_per_batch * p.tiles_n;
+  const int num_kb = ceil_div(p.K, kBK);
+  if (p.split_k <= 1) {
+    p.split_k = 1;
+    p.kb_per_split = num_kb;
+  } else {
+    B200W_CHECK_ARG(p.out_f32 && !p.bias && !p.resid && !p.gelu, "gemm: split-K writes raw fp32 partials only");
+    p.kb_per_split = ceil_div(num_kb, p.split_k);
+    p.split_k = ceil_div(num_kb, p.kb_per_split);  // no empty slices
+  }
+  const long long tiles = (long long)p.n_batch * p.tiles_m_per_batch * p.tiles_n * p.split_k;
   B200W_CHECK_ARG(tiles > 0 && tiles < (1ll << 30), "gemm: tile count out of range");
   long long g = (32ll << 20) / ((long long)kBM * p.K * 2);
   p.group_m = (int)(g < 8 ? 8 : (g > 148 ? 148 : g));

@@ -39,7 +39,10 @@ struct GemmParams {
   long long resid_ld;
   int resid_mod;
   int gelu;
+  int split_k;             // > 1: K cut into slices, slice s stores raw fp32 partials at out + s * split_stride
+  long long split_stride;  // elements between partial slabs
   // filled by the launcher
+  int kb_per_split;
   int tiles_m_per_batch, tiles_n, group_m;
 };
 
@@ -52,6 +55,9 @@ int make_tmap_a(CUtensorMap* out, const void* a, int n_batch, int rows, int K, l
 // ---------------------------------------------------------------------------------------- K4 / K10 / K9
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
                      float* out_f32, cudaStream_t stream);
+int launch_resid_ln_small(float* x, const float* part, int n_split, long long split_stride, const float* bias,
+                          const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
+                          cudaStream_t stream);
 int launch_embed(const int* tokens, int tokens_ld, const int* pos, int n_seq, int n_q, const __nv_bfloat16* tok_emb,
                  const __nv_bfloat16* pos_emb, int d, int n_ctx, float* x, cudaStream_t stream);
 
@@ -69,9 +75,12 @@ int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n
 // self attention over the paged cache: appends this step's k/v rows (taken from qkv) at pos[b] + qi first.
 int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, int n_head, const int* pos,
                                   __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, const int* block_table,
-                                  int max_pages_per_seq, int page_size, __nv_bfloat16* out, cudaStream_t stream);
+                                  int max_pages_per_seq, int page_size, __nv_bfloat16* out, cudaStream_t stream,
+                                  const float* part = nullptr, int n_split = 0, long long split_stride = 0,
+                                  const float* bias = nullptr);
 int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, int n_head,
                                    const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
-                                   __nv_bfloat16* out, cudaStream_t stream);
+                                   __nv_bfloat16* out, cudaStream_t stream, const float* part = nullptr,
+                                   int n_split = 0, long long split_stride = 0, const float* bias = nullptr);
 
 }  // namespace b200w
