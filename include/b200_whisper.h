@@ -43,6 +43,11 @@ const char* b200w_version(void);
 const char* b200w_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py reports the delta). */
 unsigned long long b200w_launch_count(void);
+/* Per-kernel timing for benchmarks: between _begin and _end every eager launch of this library is bracketed
+ * by CUDA events on its launch stream.  _end synchronises the device, writes a JSON object
+ * {"<kernel>": {"launches": n, "total_ms": t}, ...} into `json` and returns the number of launches timed. */
+int b200w_profile_begin(void);
+int b200w_profile_end(char* h_json, size_t capacity);
 
 /* ---------------------------------------------------------------------------------------------------
  * K1  log-mel front-end.  Replaces UPSTREAM audio.py::log_mel_spectrogram (+ stft, hanning, mel_filters);

@@ -52,6 +52,12 @@ def main():
         out["encoder_ms_per_window"] = ms / a.enc_windows
         flops = a.enc_windows * 2273.8e9 if a.model.startswith("large") else None
         out["encoder_tflops"] = flops / (ms * 1e-3) / 1e12 if flops else None
+        from whisper_mlx_b200._lib import kernel_profile
+
+        with kernel_profile() as prof:
+            model.encode_slabs(slabs)
+        out["encoder_kernels_ms_per_window"] = {k: {"launches": v["launches"], "ms": v["total_ms"] / a.enc_windows,
+                                                    "avg_us": v["total_ms"] / v["launches"] * 1e3} for k, v in prof.result.items()}
         e0, e1 = ev(), ev()
         e0.record()
         ckv = model.cross_kv(xa)
@@ -74,9 +80,15 @@ def main():
     torch.cuda.synchronize()
     out["prompt_step_ms"] = e0.elapsed_time(e1)
     if a.eager:
-        for _ in range(a.eager):
-            sess._step(1, -1, True)
-        torch.cuda.synchronize()
+        from whisper_mlx_b200._lib import kernel_profile
+
+        sess._step(1, -1, True)
+        with kernel_profile() as prof:
+            for _ in range(a.eager):
+                sess._step(1, -1, True)
+        out["eager_kernels_ms_per_step"] = {k: {"launches": v["launches"] // a.eager, "ms": v["total_ms"] / a.eager,
+                                                "avg_us": v["total_ms"] / v["launches"] * 1e3} for k, v in prof.result.items()}
+        out["eager_sum_ms_per_step"] = sum(v["total_ms"] for v in prof.result.values()) / a.eager
     else:
         sess.sample_step()
         torch.cuda.synchronize()

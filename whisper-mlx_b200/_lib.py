@@ -70,6 +70,8 @@ SIGNATURES = {
     "b200w_version": (C.c_char_p, []),
     "b200w_last_error": (C.c_char_p, []),
     "b200w_launch_count": (u64, []),
+    "b200w_profile_begin": (i32, []),
+    "b200w_profile_end": (i32, [C.c_char_p, sz]),
     "b200w_logmel": (i32, [vp, i32, i64, i64, i64, i32, C.POINTER(LogmelTables), vp, vp, vp]),
     "b200w_logmel_finalize": (i32, [vp, vp, i32, i64, vp]),
     "b200w_mel_windows": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp]),
@@ -132,6 +134,29 @@ def load() -> C.CDLL:
 def check(status: int) -> None:
     if status != 0:
         raise RuntimeError(f"libb200whisper error {status}: {load().b200w_last_error().decode()}")
+
+
+class kernel_profile:
+    """Context manager: CUDA-event timing of every eager kernel launch of the library inside the block.
+
+        with kernel_profile() as prof: ...
+        prof.result -> {"kernel": {"launches": n, "total_ms": t}}
+    """
+
+    def __enter__(self):
+        check(load().b200w_profile_begin())
+        self.result = {}
+        return self
+
+    def __exit__(self, *exc):
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        n = load().b200w_profile_end(buf, len(buf))
+        if n < 0:
+            check(n)
+        self.result = json.loads(buf.value.decode() or "{}")
+        return False
 
 
 def ptr(t) -> vp:

@@ -25,6 +25,39 @@ void set_last_error(const char* fmt, ...) {
 }
 const char* get_last_error() { return g_err; }
 
+// ------------------------------------------------------------------------------------------------ profiling
+struct ProfRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(const char* name, cudaStream_t s) : stream(s), slot(-1) {
+  if (!g_prof_on) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  ProfRec r{name, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, s);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].e1, stream);
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -85,7 +118,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 // C(M, ldc) = epilogue(A(M, K; lda) W(N, K)^T)
 static int gemm(const void* A, long long lda, int M, const void* W, int N, int K, void* C, long long ldc, bool out_f32,
                 const float* bias, bool gelu, const float* resid, long long resid_ld, int resid_mod,
-                cudaStream_t stream) {
+                cudaStream_t stream, const char* tag = "gemm") {
   B200W_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
   B200W_CHECK_ARG((lda * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0,
@@ -104,6 +137,7 @@ static int gemm(const void* A, long long lda, int M, const void* W, int N, int K
   p.resid_ld = resid_ld;
   p.resid_mod = resid_mod;
   p.gelu = gelu ? 1 : 0;
+  p.tag = tag;
   const int bn = gemm_block_n(1, M, N);
   CUtensorMap ta, tb;
   B200W_TRY(make_tmap_a(&ta, A, 1, M, K, lda, (long long)M * lda));
@@ -126,7 +160,7 @@ static int plan_split_k(int N, int K, int bn) {
 
 // part[s] (M, ldp) f32 = A(:, K-slice s) W(:, K-slice s)^T for s < split (the consumer kernel sums the slabs)
 static int gemm_splitk(const void* A, long long lda, int M, const void* W, int N, int K, float* part, long long ldp,
-                       long long split_stride, int split, int bn, cudaStream_t stream) {
+                       long long split_stride, int split, int bn, cudaStream_t stream, const char* tag = "gemm_splitk") {
   B200W_CHECK_ARG(M > 0 && M <= 128 && split >= 1, "gemm_splitk: needs a single row tile (M=%d)", M);
   GemmParams p{};
   p.n_batch = 1;
@@ -139,6 +173,7 @@ static int gemm_splitk(const void* A, long long lda, int M, const void* W, int N
   p.out_f32 = 1;
   p.split_k = split;
   p.split_stride = split_stride;
+  p.tag = tag;
   CUtensorMap ta, tb;
   B200W_TRY(make_tmap_a(&ta, A, 1, M, K, lda, (long long)M * lda));
   B200W_TRY(make_tmap_w(&tb, W, N, K, bn));
@@ -247,6 +282,51 @@ extern "C" {
 const char* b200w_version(void) { return "b200-whisper 0.1 (abi 1, sm_100a)"; }
 const char* b200w_last_error(void) { return get_last_error(); }
 unsigned long long b200w_launch_count(void) { return g_launch_count; }
+
+int b200w_profile_begin(void) {
+  for (auto& r : g_prof) {
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  g_prof_on = true;
+  return kOk;
+}
+
+int b200w_profile_end(char* json, size_t capacity) {
+  g_prof_on = false;
+  B200W_CUDA_OK(cudaDeviceSynchronize());
+  struct Agg {
+    const char* name;
+    int n;
+    double ms;
+  };
+  std::vector<Agg> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    bool found = false;
+    for (auto& a : agg)
+      if (strcmp(a.name, r.name) == 0) {
+        a.n++;
+        a.ms += ms;
+        found = true;
+        break;
+      }
+    if (!found) agg.push_back(Agg{r.name, 1, ms});
+  }
+  size_t off = 0;
+  auto put = [&](const char* fmt, auto... a) {
+    if (off < capacity) off += (size_t)snprintf(json + off, capacity - off, fmt, a...);
+  };
+  if (json && capacity) {
+    put("{");
+    for (size_t i = 0; i < agg.size(); ++i)
+      put("%s\"%s\": {\"launches\": %d, \"total_ms\": %.6f}", i ? ", " : "", agg[i].name, agg[i].n, agg[i].ms);
+    put("}");
+  }
+  return (int)g_prof.size();
+}
 
 int b200w_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
                  int n_mels, const b200w_logmel_tables* t, float* out_unclamped, float* gmax, void* stream) {
@@ -449,12 +529,12 @@ int b200w_encoder_forward(const b200w_model* mp, const void* mel_padded, int B, 
   for (int l = 0; l < n_layers; ++l) {
     const b200w_enc_layer& L = m.enc[l];
     B200W_TRY(launch_layernorm(x, L.attn_ln_g, L.attn_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
-    B200W_TRY(gemm(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.qkv, 3 * d, false, L.b_qkv, false, nullptr, 0, 0, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.qkv, 3 * d, false, L.b_qkv, false, nullptr, 0, 0, stream, "enc_gemm_qkv"));
     B200W_TRY(launch_encoder_attention((const __nv_bfloat16*)bf.qkv, B, T, H, (__nv_bfloat16*)bf.att, stream));
-    B200W_TRY(gemm(bf.att, d, rows, L.w_out, d, d, x, d, true, L.b_out, false, x, d, 0, stream));
+    B200W_TRY(gemm(bf.att, d, rows, L.w_out, d, d, x, d, true, L.b_out, false, x, d, 0, stream, "enc_gemm_out"));
     B200W_TRY(launch_layernorm(x, L.mlp_ln_g, L.mlp_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
-    B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));
-    B200W_TRY(gemm(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, x, d, true, L.b_mlp2, false, x, d, 0, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream, "enc_gemm_mlp1"));
+    B200W_TRY(gemm(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, x, d, true, L.b_mlp2, false, x, d, 0, stream, "enc_gemm_mlp2"));
   }
   if (stop_after_layers >= 0) {
     B200W_CHECK_ARG(xa_f32 != nullptr, "encoder_forward: probe mode needs xa_f32");
@@ -521,21 +601,21 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
       const __nv_bfloat16* ckv = static_cast<const __nv_bfloat16*>(st->cross_kv) + (size_t)l * st->cross_layer_stride;
       B200W_TRY(launch_resid_ln_small(x, bf.part_res, pend, s1, pend_bias, L.attn_ln_g, L.attn_ln_b, rows, d,
                                       (__nv_bfloat16*)bf.h, stream));
-      B200W_TRY(gemm_splitk(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.part_qkv, 3 * d, s3, sp_qkv, bn, stream));
+      B200W_TRY(gemm_splitk(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.part_qkv, 3 * d, s3, sp_qkv, bn, stream, "dec_gemm_qkv"));
       B200W_TRY(launch_decoder_self_attention(nullptr, B, 1, H, st->pos, kp, vp, st->block_table, st->max_pages,
                                               st->page_size, (__nv_bfloat16*)bf.att, stream, bf.part_qkv, sp_qkv, s3,
                                               L.b_qkv));
-      B200W_TRY(gemm_splitk(bf.att, d, rows, L.w_out, d, d, bf.part_res, d, s1, sp_d, bn, stream));
+      B200W_TRY(gemm_splitk(bf.att, d, rows, L.w_out, d, d, bf.part_res, d, s1, sp_d, bn, stream, "dec_gemm_out"));
       B200W_TRY(launch_resid_ln_small(x, bf.part_res, sp_d, s1, L.b_out, L.cross_ln_g, L.cross_ln_b, rows, d,
                                       (__nv_bfloat16*)bf.h, stream));
-      B200W_TRY(gemm_splitk(bf.h, d, rows, L.w_cq, d, d, bf.part_q, d, s1, sp_d, bn, stream));
+      B200W_TRY(gemm_splitk(bf.h, d, rows, L.w_cq, d, d, bf.part_q, d, s1, sp_d, bn, stream, "dec_gemm_cq"));
       B200W_TRY(launch_decoder_cross_attention(nullptr, B, 1, H, ckv, (long long)T * 2 * d, T, st->cross_slot,
                                                (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq));
-      B200W_TRY(gemm_splitk(bf.att, d, rows, L.w_cout, d, d, bf.part_res, d, s1, sp_d, bn, stream));
+      B200W_TRY(gemm_splitk(bf.att, d, rows, L.w_cout, d, d, bf.part_res, d, s1, sp_d, bn, stream, "dec_gemm_cout"));
       B200W_TRY(launch_resid_ln_small(x, bf.part_res, sp_d, s1, L.b_cout, L.mlp_ln_g, L.mlp_ln_b, rows, d,
                                       (__nv_bfloat16*)bf.h, stream));
-      B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));
-      B200W_TRY(gemm_splitk(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, bf.part_res, d, s1, sp_mlp2, bn, stream));
+      B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream, "dec_gemm_mlp1"));
+      B200W_TRY(gemm_splitk(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, bf.part_res, d, s1, sp_mlp2, bn, stream, "dec_gemm_mlp2"));
       pend = sp_mlp2;
       pend_bias = L.b_mlp2;
     }
@@ -574,6 +654,7 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
     p.n_store = dm.n_vocab;
     p.ldc = st->logits_ld;
     p.out_f32 = 1;
+    p.tag = "dec_gemm_logits";
     const int bn = 128;
     CUtensorMap ta, tb;
     B200W_TRY(make_tmap_w(&tb, m.w.tok_emb, dm.n_vocab, d, bn));

@@ -237,6 +237,7 @@ int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n
   B200W_TRY(encode_tmap_bf16(&tm, qkv, 3, dims, strides, box));
   B200W_TRY(init_attention());
   dim3 grid(ceil_div(T, kBQ), n_head, n_batch);
+  ProfScope prof_("encoder_attention", stream);
   encoder_attention_kernel<<<grid, kEncThreads, kEncSmem, stream>>>(tm, T, d, out);
   B200W_LAUNCH_OK();
   count_launch();
@@ -244,139 +245,157 @@ int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n
 }
 
 // =============================================================================================== K7
-constexpr int kSelfThreads = 128;
+// One WARP per (sequence, head, query): no block-level barriers, 8 lanes per key row (16 B each), 4 rows per
+// load instruction, 4 instructions in flight -- the same access pattern as K8, sized for <= 448 cached keys.
+constexpr int kSelfWarps = 8;
+constexpr int kSelfThreads = kSelfWarps * 32;
 constexpr int kMaxSelfKeys = 448;
 
-__device__ __forceinline__ int s_bt_or(const int* block_table, int b, int max_pages, int j, int page_size) {
-  return block_table[b * max_pages + j / page_size];
-}
-
 __global__ void __launch_bounds__(kSelfThreads)
-decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_q, int n_head, const int* __restrict__ pos,
-                              __nv_bfloat16* __restrict__ k_pages, __nv_bfloat16* __restrict__ v_pages,
-                              const int* __restrict__ block_table, int max_pages, int page_size,
-                              __nv_bfloat16* __restrict__ out, const float* __restrict__ part, int n_split,
-                              long long split_stride, const float* __restrict__ bias) {
-  __shared__ float s_q[kHd];
-  __shared__ float s_p[kMaxSelfKeys];
-  __shared__ float s_red[kSelfThreads / 32];
-  __shared__ float s_acc[kSelfThreads / 32][kHd];
-  __shared__ int s_bt[kMaxSelfKeys / 8];
-
-  const int h = blockIdx.x, b = blockIdx.y, qi = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, int n_q, int n_head,
+                              const int* __restrict__ pos, __nv_bfloat16* __restrict__ k_pages,
+                              __nv_bfloat16* __restrict__ v_pages, const int* __restrict__ block_table, int max_pages,
+                              int page_size, __nv_bfloat16* __restrict__ out, const float* __restrict__ part,
+                              int n_split, long long split_stride, const float* __restrict__ bias) {
+  __shared__ float s_p[kSelfWarps][kMaxSelfKeys];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * kSelfWarps + warp;  // ((b * n_head) + h) * n_q + qi
+  if (unit >= n_seq * n_head * n_q) return;
+  const int qi = unit % n_q, h = (unit / n_q) % n_head, b = unit / (n_q * n_head);
+  const int sub = lane & 7, kg = lane >> 3;
   const int d = n_head * kHd;
-  const int p0 = pos[b];             // tokens already cached for this sequence
-  const int n_keys = p0 + qi + 1;    // causal
+  const int p0 = pos[b];           // tokens already cached for this sequence
+  const int n_keys = p0 + qi + 1;  // causal
   const long long my_row = ((long long)b * n_q + qi) * 3 * d;
-
-  if (tid < max_pages) s_bt[tid] = block_table[b * max_pages + tid];
   const bool split_mode = n_split > 0;  // qkv arrives as split-K fp32 partial slabs (+ bias), n_q == 1
-  if (split_mode) {
-    // reduce the partials of this head's q / k / v slices, round to bf16 like the GEMM epilogue would have
-    for (int e = tid; e < 3 * kHd; e += kSelfThreads) {
-      const int which = e / kHd, t = e - which * kHd;
-      const long long col = (long long)which * d + h * kHd + t;
-      float v = bias[col];
-      for (int sidx = 0; sidx < n_split; ++sidx) v += part[sidx * split_stride + (long long)b * 3 * d + col];
-      const __nv_bfloat16 vb = __float2bfloat16(v);
-      if (which == 0) {
-        s_q[t] = __bfloat162float(vb) * (0.125f * kLog2e);
-      } else {
-        const long long dst = ((long long)s_bt_or(block_table, b, max_pages, p0, page_size) * page_size + p0 % page_size) * d + h * kHd + t;
-        (which == 1 ? k_pages : v_pages)[dst] = vb;
+  const int* bt = block_table + b * max_pages;
+  float* sp = s_p[warp];
+  const float c = 0.125f * kLog2e;
+
+  // ---- this token's q (registers, 8 dims per lane) and k / v rows (appended to the paged cache) ----
+  float qv[8];
+  {
+    const int j = p0 + qi;
+    const long long dst = ((long long)bt[j / page_size] * page_size + j % page_size) * d + h * kHd + sub * 8;
+    if (split_mode) {
+      // lanes 0-7 reduce q, 8-15 k, 16-23 v (8 consecutive dims each); q is then broadcast to the whole warp
+      float v8[8];
+      const int which = kg < 3 ? kg : 0;
+      const long long col = (long long)which * d + h * kHd + sub * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v8[i] = bias[col + i];
+      for (int sidx = 0; sidx < n_split; ++sidx) {
+        const float* pp = part + sidx * split_stride + (long long)b * 3 * d + col;
+        const float4 a0 = *reinterpret_cast<const float4*>(pp), a1 = *reinterpret_cast<const float4*>(pp + 4);
+        v8[0] += a0.x; v8[1] += a0.y; v8[2] += a0.z; v8[3] += a0.w;
+        v8[4] += a1.x; v8[5] += a1.y; v8[6] += a1.z; v8[7] += a1.w;
+      }
+      const uint4 packed = make_uint4(pack_bf16x2(v8[0], v8[1]), pack_bf16x2(v8[2], v8[3]), pack_bf16x2(v8[4], v8[5]),
+                                      pack_bf16x2(v8[6], v8[7]));
+      if (kg == 1) *reinterpret_cast<uint4*>(k_pages + dst) = packed;
+      if (kg == 2) *reinterpret_cast<uint4*>(v_pages + dst) = packed;
+      // q (rounded to bf16 like the GEMM epilogue would have) from lane `sub` of group 0
+      uint32_t w0 = __shfl_sync(0xffffffffu, packed.x, sub), w1 = __shfl_sync(0xffffffffu, packed.y, sub);
+      uint32_t w2 = __shfl_sync(0xffffffffu, packed.z, sub), w3 = __shfl_sync(0xffffffffu, packed.w, sub);
+      const float2 a0 = unpack_bf16x2(w0), a1 = unpack_bf16x2(w1), a2 = unpack_bf16x2(w2), a3 = unpack_bf16x2(w3);
+      qv[0] = a0.x * c; qv[1] = a0.y * c; qv[2] = a1.x * c; qv[3] = a1.y * c;
+      qv[4] = a2.x * c; qv[5] = a2.y * c; qv[6] = a3.x * c; qv[7] = a3.y * c;
+      __syncwarp();
+    } else {
+      const uint4 u = *reinterpret_cast<const uint4*>(qkv + my_row + h * kHd + sub * 8);
+      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+      qv[0] = a0.x * c; qv[1] = a0.y * c; qv[2] = a1.x * c; qv[3] = a1.y * c;
+      qv[4] = a2.x * c; qv[5] = a2.y * c; qv[6] = a3.x * c; qv[7] = a3.y * c;
+      if (kg == 1) *reinterpret_cast<uint4*>(k_pages + dst) = *reinterpret_cast<const uint4*>(qkv + my_row + d + h * kHd + sub * 8);
+      if (kg == 2) *reinterpret_cast<uint4*>(v_pages + dst) = *reinterpret_cast<const uint4*>(qkv + my_row + 2 * d + h * kHd + sub * 8);
+    }
+  }
+  // rows of position j: cached pages for j < p0 (and, in split mode, the row this warp just appended);
+  // this step's qkv rows otherwise (other warps append those concurrently)
+  auto row_ptr = [&](int j, int which) -> const __nv_bfloat16* {
+    if (j >= p0 && !split_mode) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + (long long)which * d + h * kHd + sub * 8;
+    const __nv_bfloat16* base = which == 1 ? k_pages : v_pages;
+    return base + ((long long)bt[j / page_size] * page_size + j % page_size) * d + h * kHd + sub * 8;
+  };
+
+  // ---- scores ----
+  float mx = -INFINITY;
+  for (int j0 = kg; j0 < n_keys; j0 += 16) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + 4 * i;
+      u[i] = (j < n_keys) ? *reinterpret_cast<const uint4*>(row_ptr(j, 1)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + 4 * i;
+      const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z), a3 = unpack_bf16x2(u[i].w);
+      float sc = a0.x * qv[0];
+      sc = fmaf(a0.y, qv[1], sc);
+      sc = fmaf(a1.x, qv[2], sc);
+      sc = fmaf(a1.y, qv[3], sc);
+      sc = fmaf(a2.x, qv[4], sc);
+      sc = fmaf(a2.y, qv[5], sc);
+      sc = fmaf(a3.x, qv[6], sc);
+      sc = fmaf(a3.y, qv[7], sc);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+      sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+      if (j < n_keys) {
+        if (sub == 0) sp[j] = sc;
+        mx = fmaxf(mx, sc);
       }
     }
-  } else if (tid >= 64) {
-    s_q[tid - 64] = __bfloat162float(qkv[my_row + h * kHd + tid - 64]) * (0.125f * kLog2e);
-  }
-  __syncthreads();
-
-  // append this token's k / v rows to the paged cache (each (b, h, qi) block owns its 64-wide slice)
-  if (!split_mode && tid < 16) {
-    const int j = p0 + qi;
-    const long long dst = ((long long)s_bt[j / page_size] * page_size + j % page_size) * d + h * kHd;
-    const uint4* ks = reinterpret_cast<const uint4*>(qkv + my_row + d + h * kHd);
-    const uint4* vs = reinterpret_cast<const uint4*>(qkv + my_row + 2 * d + h * kHd);
-    if (tid < 8) reinterpret_cast<uint4*>(k_pages + dst)[tid] = ks[tid];
-    else reinterpret_cast<uint4*>(v_pages + dst)[tid - 8] = vs[tid - 8];
-  }
-
-  // rows of position j: cached pages for j < p0, this step's qkv rows otherwise (other blocks write those)
-  auto k_row = [&](int j) -> const __nv_bfloat16* {
-    if (j >= p0 && !split_mode) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + d + h * kHd;
-    return k_pages + ((long long)s_bt[j / page_size] * page_size + j % page_size) * d + h * kHd;
-  };
-  auto v_row = [&](int j) -> const __nv_bfloat16* {
-    if (j >= p0 && !split_mode) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + 2 * d + h * kHd;
-    return v_pages + ((long long)s_bt[j / page_size] * page_size + j % page_size) * d + h * kHd;
-  };
-
-  // scores: one key row (128 B = 8 x 16 B independent loads) per thread
-  float mx = -INFINITY;
-  for (int j = tid; j < n_keys; j += kSelfThreads) {
-    const uint4* kr = reinterpret_cast<const uint4*>(k_row(j));
-    uint4 u[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) u[c] = kr[c];
-    float acc = 0.0f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float2 a0 = unpack_bf16x2(u[c].x), a1 = unpack_bf16x2(u[c].y), a2 = unpack_bf16x2(u[c].z), a3 = unpack_bf16x2(u[c].w);
-      acc = fmaf(a0.x, s_q[8 * c + 0], acc);
-      acc = fmaf(a0.y, s_q[8 * c + 1], acc);
-      acc = fmaf(a1.x, s_q[8 * c + 2], acc);
-      acc = fmaf(a1.y, s_q[8 * c + 3], acc);
-      acc = fmaf(a2.x, s_q[8 * c + 4], acc);
-      acc = fmaf(a2.y, s_q[8 * c + 5], acc);
-      acc = fmaf(a3.x, s_q[8 * c + 6], acc);
-      acc = fmaf(a3.y, s_q[8 * c + 7], acc);
-    }
-    s_p[j] = acc;
-    mx = fmaxf(mx, acc);
   }
   mx = warp_max(mx);
-  if (lane == 0) s_red[warp] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-  __syncthreads();
+  __syncwarp();
   float sum = 0.0f;
-  for (int j = tid; j < n_keys; j += kSelfThreads) {
-    const float p = fast_exp2(s_p[j] - mx);
+  for (int j = lane; j < n_keys; j += 32) {
+    const float p = fast_exp2(sp[j] - mx);
     sum += p;
-    s_p[j] = __bfloat162float(__float2bfloat16(p));  // bf16 probabilities, as in the tensor-core path
+    sp[j] = __bfloat162float(__float2bfloat16(p));  // bf16 probabilities, as in the tensor-core path
   }
   sum = warp_sum(sum);
-  if (lane == 0) s_red[warp] = sum;
-  __syncthreads();
-  sum = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+  __syncwarp();
 
-  // output: warp w takes keys w, w+4, ...; a lane owns two of the 64 dims (one coalesced 128 B row per load),
-  // eight rows in flight per warp
-  float acc0 = 0.0f, acc1 = 0.0f;
-  for (int j0 = warp; j0 < n_keys; j0 += 4 * 8) {
-    uint32_t u[8];
-    float p[8];
+  // ---- output ----
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int j0 = kg; j0 < n_keys; j0 += 16) {
+    uint4 u[4];
+    float p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
       const int j = j0 + 4 * i;
       const bool ok = j < n_keys;
-      u[i] = ok ? reinterpret_cast<const uint32_t*>(v_row(j))[lane] : 0u;
-      p[i] = ok ? s_p[j] : 0.0f;
+      u[i] = ok ? *reinterpret_cast<const uint4*>(row_ptr(j, 2)) : make_uint4(0, 0, 0, 0);
+      p[i] = ok ? sp[j] : 0.0f;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 v = unpack_bf16x2(u[i]);
-      acc0 = fmaf(p[i], v.x, acc0);
-      acc1 = fmaf(p[i], v.y, acc1);
+    for (int i = 0; i < 4; ++i) {
+      const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z), a3 = unpack_bf16x2(u[i].w);
+      acc[0] = fmaf(p[i], a0.x, acc[0]);
+      acc[1] = fmaf(p[i], a0.y, acc[1]);
+      acc[2] = fmaf(p[i], a1.x, acc[2]);
+      acc[3] = fmaf(p[i], a1.y, acc[3]);
+      acc[4] = fmaf(p[i], a2.x, acc[4]);
+      acc[5] = fmaf(p[i], a2.y, acc[5]);
+      acc[6] = fmaf(p[i], a3.x, acc[6]);
+      acc[7] = fmaf(p[i], a3.y, acc[7]);
     }
   }
-  s_acc[warp][2 * lane] = acc0;
-  s_acc[warp][2 * lane + 1] = acc1;
-  __syncthreads();
-  if (tid < kHd) {
-    const float v = (s_acc[0][tid] + s_acc[1][tid] + s_acc[2][tid] + s_acc[3][tid]) / sum;
-    out[((long long)b * n_q + qi) * d + h * kHd + tid] = __float2bfloat16(v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (kg == 0) {
+    const float inv = 1.0f / sum;
+    *reinterpret_cast<uint4*>(out + ((long long)b * n_q + qi) * d + h * kHd + sub * 8) =
+        make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                   pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
   }
 }
 
@@ -386,12 +405,13 @@ int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, 
                                   const float* part, int n_split, long long split_stride, const float* bias) {
   B200W_CHECK_ARG(n_split == 0 || (n_q == 1 && part && bias), "self_attention: split-K input needs n_q == 1");
   B200W_CHECK_ARG(n_split > 0 || qkv, "self_attention: null qkv");
-  B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "self_attention: bad sizes");
+  B200W_CHECK_ARG(n_seq > 0 && n_q > 0 && (long long)n_seq * n_q * n_head < (1ll << 30), "self_attention: bad sizes");
   B200W_CHECK_ARG(max_pages_per_seq * page_size <= kMaxSelfKeys, "self_attention: context above %d", kMaxSelfKeys);
-  dim3 grid(n_head, n_seq, n_q);
-  decoder_self_attention_kernel<<<grid, kSelfThreads, 0, stream>>>(qkv, n_q, n_head, pos, k_pages, v_pages,
-                                                                   block_table, max_pages_per_seq, page_size, out,
-                                                                   part, n_split, split_stride, bias);
+  const int units = n_seq * n_head * n_q;
+  ProfScope prof_("decoder_self_attention", stream);
+  decoder_self_attention_kernel<<<ceil_div(units, kSelfWarps), kSelfThreads, 0, stream>>>(
+      qkv, n_seq, n_q, n_head, pos, k_pages, v_pages, block_table, max_pages_per_seq, page_size, out, part, n_split,
+      split_stride, bias);
   B200W_LAUNCH_OK();
   count_launch();
   return kOk;
@@ -549,6 +569,7 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
   B200W_CHECK_ARG(n_split > 0 ? (part && bias) : (q != nullptr), "cross_attention: missing query input");
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
   dim3 grid(n_head, n_seq, n_q);
+  ProfScope prof_("decoder_cross_attention", stream);
   decoder_cross_attention_kernel<<<grid, kCrossThreads, 0, stream>>>(q, n_q, n_head, cross_kv, seq_stride, T, slot,
                                                                      out, part, n_split, split_stride, bias);
   B200W_LAUNCH_OK();

@@ -63,6 +63,15 @@ const char* get_last_error();
 extern unsigned long long g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
 
+// Optional per-launch timing (b200w_profile_begin/_end): CUDA events recorded on the launch stream around every
+// kernel launch, aggregated by kernel name.  Eager launches only (not during stream capture).
+struct ProfScope {
+  cudaStream_t stream;
+  int slot;
+  ProfScope(const char* name, cudaStream_t s);
+  ~ProfScope();
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -62,6 +62,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
                      float* out_f32, cudaStream_t stream) {
   B200W_CHECK_ARG(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * kLnMaxVec, "layernorm: unsupported d=%d", d);
+  ProfScope prof_("layernorm", stream);
   layernorm_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_f32);
   B200W_LAUNCH_OK();
   count_launch();
@@ -112,6 +113,7 @@ int launch_resid_ln_small(float* x, const float* part, int n_split, long long sp
                           cudaStream_t stream) {
   B200W_CHECK_ARG(rows > 0 && d % 128 == 0 && d <= 1280, "resid_ln: unsupported d=%d", d);
   B200W_CHECK_ARG(n_split == 0 || (part != nullptr && bias != nullptr), "resid_ln: partials without bias");
+  ProfScope prof_("resid_ln", stream);
   resid_ln_small_kernel<<<rows, d / 4, 0, stream>>>(x, part, n_split, split_stride, bias, gamma, beta, d, out_bf16);
   B200W_LAUNCH_OK();
   count_launch();
@@ -139,6 +141,7 @@ __global__ void embed_kernel(const int* __restrict__ tokens, int tokens_ld, cons
 int launch_embed(const int* tokens, int tokens_ld, const int* pos, int n_seq, int n_q, const __nv_bfloat16* tok_emb,
                  const __nv_bfloat16* pos_emb, int d, int n_ctx, float* x, cudaStream_t stream) {
   B200W_CHECK_ARG(n_seq > 0 && n_q > 0 && d % 2 == 0, "embed: bad sizes");
+  ProfScope prof_("embed", stream);
   embed_kernel<<<n_seq * n_q, 128, 0, stream>>>(tokens, tokens_ld, pos, n_q, tok_emb, pos_emb, d, n_ctx, x);
   B200W_LAUNCH_OK();
   count_launch();
@@ -331,6 +334,7 @@ filter_argmax_kernel(const float* __restrict__ logits, const uint32_t* __restric
 int launch_filter_argmax(const float* logits, const uint32_t* suppress_bits, int* tokens, int* n_tokens, int* pos,
                          float* sum_logprob, int* finished, int n_seq, const FilterParams& fp, cudaStream_t stream) {
   B200W_CHECK_ARG(n_seq > 0 && fp.n_vocab > 0 && fp.logits_ld >= fp.n_vocab, "filter_argmax: bad sizes");
+  ProfScope prof_("filter_argmax", stream);
   filter_argmax_kernel<<<n_seq, kFaThreads, 0, stream>>>(logits, suppress_bits, tokens, n_tokens, pos, sum_logprob,
                                                          finished, fp);
   B200W_LAUNCH_OK();
@@ -365,6 +369,7 @@ no_speech_kernel(const float* __restrict__ logits, int logits_ld, int n_vocab, i
 
 int launch_no_speech(const float* logits, int logits_ld, int n_seq, int n_vocab, int no_speech, float* out,
                      cudaStream_t stream) {
+  ProfScope prof_("no_speech", stream);
   no_speech_kernel<<<n_seq, 1024, 0, stream>>>(logits, logits_ld, n_vocab, no_speech, out);
   B200W_LAUNCH_OK();
   count_launch();
@@ -388,6 +393,7 @@ __global__ void language_kernel(const float* __restrict__ logits, int logits_ld,
 
 int launch_language(const float* logits, int logits_ld, int n_seq, int lang_begin, int n_lang, int* lang_token,
                     float* lang_probs, cudaStream_t stream) {
+  ProfScope prof_("language", stream);
   language_kernel<<<n_seq, 32, 0, stream>>>(logits, logits_ld, lang_begin, n_lang, lang_token, lang_probs);
   B200W_LAUNCH_OK();
   count_launch();

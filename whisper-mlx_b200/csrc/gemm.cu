@@ -274,6 +274,7 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, GemmPara
   long long g = (32ll << 20) / ((long long)kBM * p.K * 2);
   p.group_m = (int)(g < 8 ? 8 : (g > 148 ? 148 : g));
   const int grid = (int)(tiles < device_sm_count() ? tiles : device_sm_count());
+  ProfScope prof_(p.tag ? p.tag : "gemm", stream);
   gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   B200W_LAUNCH_OK();
   count_launch();

@@ -41,6 +41,7 @@ struct GemmParams {
   int gelu;
   int split_k;             // > 1: K cut into slices, slice s stores raw fp32 partials at out + s * split_stride
   long long split_stride;  // elements between partial slabs
+  const char* tag;         // profile label (null: "gemm")
   // filled by the launcher
   int kb_per_split;
   int tiles_m_per_batch, tiles_n, group_m;

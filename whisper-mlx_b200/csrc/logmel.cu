@@ -18,11 +18,13 @@ namespace b200w {
 constexpr int kNfft = 400;
 constexpr int kHop = 160;
 constexpr int kBins = 201;
-constexpr int kFrames = 16;             // frames per CTA
-constexpr int kPairs = kFrames / 2;     // complex transforms per CTA
-constexpr int kTile = (kFrames - 1) * kHop + kNfft;  // 2800 samples incl. halo
-constexpr int kLmThreads = 128;
-constexpr int kPowStride = 208;         // floats per power spectrum row
+constexpr int kFrames = 32;             // frames per CTA
+constexpr int kPairs = kFrames / 2;     // complex transforms per CTA (two real frames each)
+constexpr int kTile = (kFrames - 1) * kHop + kNfft;  // 5360 samples incl. halo
+constexpr int kLmThreads = 256;
+constexpr int kPowStride = 203;         // floats per power-spectrum row; odd => conflict-free lane-per-frame reads
+constexpr int kOutStride = 129;         // floats per staged output row (n_mels <= 128), odd for the same reason
+constexpr int kRegion0Floats = (kFrames * kPowStride > kTile ? kFrames * kPowStride : kTile);
 
 struct LogmelTables {
   const float* hann;      // [400] periodic Hann
@@ -33,18 +35,20 @@ struct LogmelTables {
   const float* mel_w;     // flattened non-zero weights
 };
 
-__global__ void __launch_bounds__(kLmThreads)
+// Shared memory plan (76.5 KB, two CTAs per SM):
+//   region 0 : sample tile with halo (phases 0-1)   -> power spectra [32][203] (phases 3-5)
+//   region 1 : FFT work [16 pairs][400] complex      -> staged log-mel rows [32][129] (phase 5)
+__global__ void __launch_bounds__(kLmThreads, 2)
 logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n_valid, long long n_total,
               int n_frames, int n_mels, LogmelTables tb, float* __restrict__ out, float* __restrict__ gmax) {
   extern __shared__ __align__(16) unsigned char lm_smem[];
-  // region 0: sample tile (phase 0-1), later the power spectra (phase 4-5)
   float* s_samples = reinterpret_cast<float*>(lm_smem);
   float* s_power = reinterpret_cast<float*>(lm_smem);
-  constexpr int kRegion0 = (kPairs * 2 * kPowStride > kTile ? kPairs * 2 * kPowStride : kTile);
-  lm::cpx* s_work = reinterpret_cast<lm::cpx*>(lm_smem + sizeof(float) * kRegion0);  // [kPairs][400]
+  lm::cpx* s_work = reinterpret_cast<lm::cpx*>(lm_smem + sizeof(float) * kRegion0Floats);
+  float* s_out = reinterpret_cast<float*>(s_work);
   __shared__ float s_red[kLmThreads / 32];
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int audio = blockIdx.y;
   const int f0 = blockIdx.x * kFrames;
   const float* x = pcm + (long long)audio * audio_stride;
@@ -67,74 +71,93 @@ logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n
   __syncthreads();
 
   // ---- phase 1: 25 column DFT-16 per pair + W400 twiddle ------------------------------------------
-  for (int item = tid; item < kPairs * 25; item += kLmThreads) {
-    const int p = item / 25, n2 = item - p * 25;
-    const float* fa = s_samples + (2 * p) * kHop;
-    const float* fb = fa + kHop;
-    lm::cpx a[16];
+  // thread t < 250 owns column n2 = t % 25 for pairs t / 25 and t / 25 + 10: window and twiddles stay in registers
+  if (tid < 250) {
+    const int n2 = tid % 25, g = tid / 25;
+    float hw[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-      const int n = 25 * n1 + n2;
-      const float w = __ldg(tb.hann + n);
-      a[n1].re = w * fa[n];
-      a[n1].im = w * fb[n];
-    }
-    lm::dft16(a);
-    const float4* tw = reinterpret_cast<const float4*>(tb.tw400 + n2 * 16);
-    lm::cpx* dst = s_work + p * kNfft + n2;
+    for (int n1 = 0; n1 < 16; ++n1) hw[n1] = __ldg(tb.hann + 25 * n1 + n2);
+    float4 tw[8];
+    const float4* twp = reinterpret_cast<const float4*>(tb.tw400 + n2 * 16);
 #pragma unroll
-    for (int k1 = 0; k1 < 16; k1 += 2) {
-      const float4 t = __ldg(tw + (k1 >> 1));
-      dst[(k1 + 0) * 25] = lm::cmul(a[k1 + 0], lm::cpx{t.x, t.y});
-      dst[(k1 + 1) * 25] = lm::cmul(a[k1 + 1], lm::cpx{t.z, t.w});
+    for (int i = 0; i < 8; ++i) tw[i] = __ldg(twp + i);
+#pragma unroll 1
+    for (int p = g; p < kPairs; p += 10) {
+      const float* fa = s_samples + (2 * p) * kHop + n2;
+      const float* fb = fa + kHop;
+      lm::cpx a[16];
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        a[n1].re = hw[n1] * fa[25 * n1];
+        a[n1].im = hw[n1] * fb[25 * n1];
+      }
+      lm::dft16(a);
+      lm::cpx* dst = s_work + p * kNfft + n2;
+#pragma unroll
+      for (int k1 = 0; k1 < 16; k1 += 2) {
+        dst[(k1 + 0) * 25] = lm::cmul(a[k1 + 0], lm::cpx{tw[k1 >> 1].x, tw[k1 >> 1].y});
+        dst[(k1 + 1) * 25] = lm::cmul(a[k1 + 1], lm::cpx{tw[k1 >> 1].z, tw[k1 >> 1].w});
+      }
     }
   }
   __syncthreads();
 
-  // ---- phase 2/3: 16 row DFT-25 per pair (read rows, sync, scatter to natural order) ---------------
+  // ---- phase 3: 16 row DFT-25 per pair; split the two real spectra in registers -------------------------
+  // thread (p, k1) ends with Z[k1 + 16*k2], k2 < 25.  The conjugate partner Z[400 - k] of its bins k <= 200 lives
+  // in lane (16 - k1) % 16 of the same half-warp at register 24 - k2 (k1 == 0: own register 25 - k2), so
+  // |Xa|^2, |Xb|^2 need one shuffle pair per bin instead of a round trip through shared memory.
   {
     static_assert(kPairs * 16 == kLmThreads, "one DFT-25 per thread");
     const int p = tid >> 4, k1 = tid & 15;
-    lm::cpx* row = s_work + p * kNfft;
+    const lm::cpx* row = s_work + p * kNfft + k1 * 25;
     lm::cpx a[25];
 #pragma unroll
-    for (int n2 = 0; n2 < 25; ++n2) a[n2] = row[k1 * 25 + n2];
+    for (int n2 = 0; n2 < 25; ++n2) a[n2] = row[n2];
     lm::dft25(a);
-    __syncthreads();
+    const int partner = (lane & 16) | ((16 - k1) & 15);
+    float* pa = s_power + (2 * p) * kPowStride + k1;
+    float* pb = pa + kPowStride;
 #pragma unroll
-    for (int k2 = 0; k2 < 25; ++k2) row[k1 + 16 * k2] = a[k2];
+    for (int k2 = 0; k2 <= 12; ++k2) {
+      const float sre = __shfl_sync(0xffffffffu, a[24 - k2].re, partner);
+      const float sim = __shfl_sync(0xffffffffu, a[24 - k2].im, partner);
+      const lm::cpx own = a[(25 - k2) % 25];
+      const float zr = (k1 == 0) ? own.re : sre, zi = (k1 == 0) ? own.im : sim;
+      const float ar = a[k2].re + zr, ai = a[k2].im - zi;
+      const float br = a[k2].re - zr, bi = a[k2].im + zi;
+      if (k1 + 16 * k2 <= 200) {
+        pa[16 * k2] = 0.25f * (ar * ar + ai * ai);
+        pb[16 * k2] = 0.25f * (br * br + bi * bi);
+      }
+    }
   }
   __syncthreads();
 
-  // ---- phase 4: split the two real spectra, power ----------------------------------------------
-  for (int item = tid; item < kPairs * kBins; item += kLmThreads) {
-    const int p = item / kBins, k = item - p * kBins;
-    const lm::cpx zk = s_work[p * kNfft + k];
-    const lm::cpx zn = s_work[p * kNfft + ((kNfft - k) % kNfft)];
-    const float ar = zk.re + zn.re, ai = zk.im - zn.im;
-    const float br = zk.re - zn.re, bi = zk.im + zn.im;
-    s_power[(2 * p) * kPowStride + k] = 0.25f * (ar * ar + ai * ai);
-    s_power[(2 * p + 1) * kPowStride + k] = 0.25f * (br * br + bi * bi);
-  }
-  __syncthreads();
-
-  // ---- phase 5: sparse mel, log10, store, running max ----------------------------------------------
+  // ---- phase 5: sparse mel with one lane per frame, log10, staged rows, running max ---------------------
+  // every lane of a warp walks the same (mel, bin) sequence: no divergence, weights are warp-uniform loads
   float vmax = -INFINITY;
+  {
+    const float* pw = s_power + lane * kPowStride;  // lane == frame within the tile
+    float* so = s_out + lane * kOutStride;
+    for (int m = warp; m < n_mels; m += kLmThreads / 32) {
+      const int lo = __ldg(tb.mel_lo + m), cnt = __ldg(tb.mel_cnt + m);
+      const float* w = tb.mel_w + __ldg(tb.mel_off + m);
+      float acc = 0.0f;
+      for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(w + j), pw[lo + j], acc);
+      const float v = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));
+      so[m] = v;
+      if (f0 + lane < n_frames) vmax = fmaxf(vmax, v);
+    }
+  }
+  __syncthreads();
   const int valid_frames = min(kFrames, n_frames - f0);
   float* o = out + ((long long)audio * n_frames + f0) * n_mels;
   for (int item = tid; item < valid_frames * n_mels; item += kLmThreads) {
     const int f = item / n_mels, m = item - f * n_mels;
-    const int lo = __ldg(tb.mel_lo + m), cnt = __ldg(tb.mel_cnt + m);
-    const float* w = tb.mel_w + __ldg(tb.mel_off + m);
-    const float* pw = s_power + f * kPowStride + lo;
-    float acc = 0.0f;
-    for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(w + j), pw[j], acc);
-    const float v = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));
-    o[item] = v;
-    vmax = fmaxf(vmax, v);
+    o[item] = s_out[f * kOutStride + m];
   }
   vmax = warp_max(vmax);
-  if ((tid & 31) == 0) s_red[tid >> 5] = vmax;
+  if (lane == 0) s_red[warp] = vmax;
   __syncthreads();
   if (tid == 0) {
     float m = s_red[0];
@@ -200,8 +223,8 @@ __global__ void mel_window_kernel(const float* __restrict__ mel, const float* __
 
 // ---------------------------------------------------------------------------------------------- host
 static size_t logmel_smem_bytes() {
-  constexpr int kRegion0 = (kPairs * 2 * kPowStride > kTile ? kPairs * 2 * kPowStride : kTile);
-  return sizeof(float) * kRegion0 + sizeof(lm::cpx) * kPairs * kNfft;
+  static_assert(sizeof(lm::cpx) * kPairs * kNfft >= sizeof(float) * kFrames * kOutStride, "staged rows fit the work area");
+  return sizeof(float) * kRegion0Floats + sizeof(lm::cpx) * kPairs * kNfft;
 }
 
 int init_logmel() {
@@ -222,6 +245,7 @@ int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long lo
   const int n_frames = (int)n_frames_ll;
   const size_t smem = logmel_smem_bytes();
   B200W_TRY(init_logmel());
+  ProfScope prof_("logmel", stream);
   fill_f32_kernel<<<ceil_div(n_audio, 256), 256, 0, stream>>>(gmax, -INFINITY, n_audio);
   B200W_LAUNCH_OK();
   LogmelTables tb{hann, reinterpret_cast<const float2*>(tw400), mel_lo, mel_cnt, mel_off, mel_w};
@@ -237,6 +261,7 @@ int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long lo
 int launch_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, cudaStream_t stream) {
   const long long total = per_audio * n_audio;
   const long long nthreads = ceil_div_ll(total, 4);
+  ProfScope prof_("logmel_finalize", stream);
   logmel_finalize_kernel<<<(unsigned)ceil_div_ll(nthreads, 256), 256, 0, stream>>>(x, gmax, per_audio, total);
   B200W_LAUNCH_OK();
   count_launch();
@@ -247,6 +272,7 @@ int launch_mel_windows(const float* mel, const float* gmax, const long long* row
                        int n_windows, int n_mels, __nv_bfloat16* dst, cudaStream_t stream) {
   B200W_CHECK_ARG(n_mels % 2 == 0 && n_windows > 0 && n_windows <= 65535, "mel_windows: bad sizes");
   dim3 grid(ceil_div(3002 * n_mels / 2, 256), n_windows);
+  ProfScope prof_("mel_windows", stream);
   mel_window_kernel<<<grid, 256, 0, stream>>>(mel, gmax, row0, size, gidx, n_mels, dst);
   B200W_LAUNCH_OK();
   count_launch();
