@@ -56,11 +56,9 @@ int b200w_profile_end(char* h_json, size_t capacity);
 typedef struct {
   const float* hann;   /* [400] periodic Hann window                                  */
   const float* tw400;  /* [25][16][2] twiddles W400^(n2*k1) as (cos, -sin)             */
-  const int* mel_lo;   /* [n_mels] first frequency bin of each filter's support        */
-  const int* mel_cnt;  /* [n_mels] number of bins in the (contiguous) support          */
-  const int* mel_off;  /* [n_mels] offset of the filter's weights inside mel_w         */
-  const float* mel_w;  /* flattened weights of the supports                            */
 } b200w_logmel_tables;
+/* The mel filterbank itself (slaney scale and norm, n_mels in {80, 128}, = the reference's
+ * assets/mel_filters.npz) is compiled into the kernel (csrc/mel_tables.h, tools/gen_mel_tables.py). */
 
 /* pcm: n_audio signals of n_valid f32 samples, audio_stride samples apart.  Each signal is zero-extended
  * to n_total samples (the `padding` argument of the reference), reflect-padded by 200 and framed with

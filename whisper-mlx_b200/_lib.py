@@ -25,7 +25,7 @@ sz = C.c_size_t
 
 
 class LogmelTables(C.Structure):
-    _fields_ = [("hann", vp), ("tw400", vp), ("mel_lo", vp), ("mel_cnt", vp), ("mel_off", vp), ("mel_w", vp)]
+    _fields_ = [("hann", vp), ("tw400", vp)]
 
 
 class FilterParams(C.Structure):

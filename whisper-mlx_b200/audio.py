@@ -126,28 +126,18 @@ def hanning(size: int) -> np.ndarray:
 
 
 class _Tables:
-    """Device-resident constant tables of the log-mel kernel for one (device, n_mels)."""
+    """Device-resident constant tables of the log-mel kernel (window, FFT twiddles) for one device.
+
+    The mel filterbank is compiled into the kernel (csrc/mel_tables.h, generated from `mel_filters`)."""
 
     def __init__(self, device: torch.device, n_mels: int):
-        fb = mel_filters(n_mels)
-        lo, cnt, off, w = [], [], [], []
-        for m in range(n_mels):
-            nz = np.nonzero(fb[m])[0]
-            a, b = (int(nz[0]), int(nz[-1]) + 1) if len(nz) else (0, 0)
-            lo.append(a)
-            cnt.append(b - a)
-            off.append(len(w))
-            w.extend(fb[m, a:b].tolist())
         n2, k1 = np.arange(25)[:, None], np.arange(16)[None, :]
         ang = -2.0 * np.pi * (n2 * k1) / 400.0
         tw = np.stack([np.cos(ang), np.sin(ang)], axis=-1).astype(np.float32)
         t = lambda a, dt: torch.tensor(np.asarray(a), dtype=dt, device=device)  # noqa: E731
         self.hann = t(hanning(N_FFT).astype(np.float32), torch.float32)
         self.tw = t(tw, torch.float32)
-        self.lo, self.cnt, self.off = t(lo, torch.int32), t(cnt, torch.int32), t(off, torch.int32)
-        self.w = t(np.asarray(w, dtype=np.float32), torch.float32)
-        self.struct = _lib.LogmelTables(_lib.ptr(self.hann), _lib.ptr(self.tw), _lib.ptr(self.lo),
-                                        _lib.ptr(self.cnt), _lib.ptr(self.off), _lib.ptr(self.w))
+        self.struct = _lib.LogmelTables(_lib.ptr(self.hann), _lib.ptr(self.tw))
 
 
 _tables = {}

@@ -331,8 +331,8 @@ int b200w_profile_end(char* json, size_t capacity) {
 int b200w_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
                  int n_mels, const b200w_logmel_tables* t, float* out_unclamped, float* gmax, void* stream) {
   B200W_CHECK_ARG(pcm && t && out_unclamped && gmax, "logmel: null pointer");
-  return launch_logmel(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, t->hann, t->tw400, t->mel_lo, t->mel_cnt,
-                       t->mel_off, t->mel_w, out_unclamped, gmax, (cudaStream_t)stream);
+  return launch_logmel(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, t->hann, t->tw400, out_unclamped, gmax,
+                       (cudaStream_t)stream);
 }
 
 int b200w_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, void* stream) {

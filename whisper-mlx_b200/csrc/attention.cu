@@ -320,16 +320,16 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
 
   // ---- scores ----
   float mx = -INFINITY;
-  for (int j0 = kg; j0 < n_keys; j0 += 16) {
+  for (int j0 = 0; j0 < n_keys; j0 += 16) {  // warp-uniform trip count: the shuffles below need every lane
     uint4 u[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int j = j0 + 4 * i;
+      const int j = j0 + kg + 4 * i;
       u[i] = (j < n_keys) ? *reinterpret_cast<const uint4*>(row_ptr(j, 1)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int j = j0 + 4 * i;
+      const int j = j0 + kg + 4 * i;
       const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z), a3 = unpack_bf16x2(u[i].w);
       float sc = a0.x * qv[0];
       sc = fmaf(a0.y, qv[1], sc);
@@ -363,12 +363,12 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-  for (int j0 = kg; j0 < n_keys; j0 += 16) {
+  for (int j0 = 0; j0 < n_keys; j0 += 16) {
     uint4 u[4];
     float p[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int j = j0 + 4 * i;
+      const int j = j0 + kg + 4 * i;
       const bool ok = j < n_keys;
       u[i] = ok ? *reinterpret_cast<const uint4*>(row_ptr(j, 2)) : make_uint4(0, 0, 0, 0);
       p[i] = ok ? sp[j] : 0.0f;
@@ -467,16 +467,16 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   // ---- scores: 4 keys per warp per load instruction, 4 loads in flight per thread ----
   constexpr int kStep = kCrossWarps * 4;  // keys per CTA sweep
   float mx = -INFINITY;
-  for (int j0 = warp * 4 + kg; j0 < T; j0 += 4 * kStep) {
+  for (int j0 = warp * 4; j0 < T; j0 += 4 * kStep) {  // warp-uniform trip count: the shuffles need every lane
     uint4 u[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int j = j0 + i * kStep;
+      const int j = j0 + kg + i * kStep;
       u[i] = (j < T) ? __ldg(reinterpret_cast<const uint4*>(kbase + j * ld)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int j = j0 + i * kStep;
+      const int j = j0 + kg + i * kStep;
       const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z),
                    a3 = unpack_bf16x2(u[i].w);
       float s = a0.x * qv[0];
@@ -520,12 +520,12 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-  for (int j0 = warp * 4 + kg; j0 < T; j0 += 4 * kStep) {
+  for (int j0 = warp * 4; j0 < T; j0 += 4 * kStep) {
     uint4 u[4];
     float p[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int j = j0 + i * kStep;
+      const int j = j0 + kg + i * kStep;
       u[i] = (j < T) ? __ldg(reinterpret_cast<const uint4*>(vbase + j * ld)) : make_uint4(0, 0, 0, 0);
       p[i] = (j < T) ? s_p[j] : 0.0f;
     }

@@ -17,8 +17,8 @@ int init_logmel();
 
 // ---------------------------------------------------------------------------------------- K1 log-mel
 int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
-                  int n_mels, const float* hann, const float* tw400, const int* mel_lo, const int* mel_cnt,
-                  const int* mel_off, const float* mel_w, float* out_unclamped, float* gmax, cudaStream_t stream);
+                  int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
+                  cudaStream_t stream);
 int launch_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, cudaStream_t stream);
 int launch_mel_windows(const float* mel, const float* gmax, const long long* row0, const int* size, const int* gidx,
                        int n_windows, int n_mels, __nv_bfloat16* dst, cudaStream_t stream);

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "logmel_core.h"
+#include "mel_tables.h"
 
 namespace b200w {
 
@@ -24,23 +25,41 @@ constexpr int kTile = (kFrames - 1) * kHop + kNfft;  // 5360 samples incl. halo
 constexpr int kLmThreads = 256;
 constexpr int kPowStride = 203;         // floats per power-spectrum row; odd => conflict-free lane-per-frame reads
 constexpr int kOutStride = 129;         // floats per staged output row (n_mels <= 128), odd for the same reason
+constexpr int kPairStride = 409;        // complex elements between the FFT work areas of two pairs (400 + bank skew)
 constexpr int kRegion0Floats = (kFrames * kPowStride > kTile ? kFrames * kPowStride : kTile);
 
 struct LogmelTables {
   const float* hann;      // [400] periodic Hann
   const float2* tw400;    // [25][16] W400^(n2*k1)
-  const int* mel_lo;      // [n_mels] first bin
-  const int* mel_cnt;     // [n_mels] bins in the contiguous support
-  const int* mel_off;     // [n_mels] offset into mel_w
-  const float* mel_w;     // flattened non-zero weights
 };
+
+// Sparse mel stage for the mels m = W, W + 8, ... of one warp; lane == frame.  The filterbank is a compile-time
+// table (mel_tables.h): after unrolling every weight is an FFMA immediate and every power-spectrum read an LDS
+// with an immediate offset -- no table loads, no loop overhead, no divergence.
+template <int NM, int W>
+__device__ __forceinline__ void mel_for_warp(const float* __restrict__ pw, float* __restrict__ so, float& vmax) {
+  using Bank = lm::MelBank<NM>;
+#pragma unroll
+  for (int i = 0; i < (NM - W + 7) / 8; ++i) {
+    const int m = W + 8 * i;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < Bank::kMaxCnt; ++j)
+      if (j < Bank::cnt(m)) acc = fmaf(Bank::w(Bank::off(m) + j), pw[Bank::lo(m) + j], acc);
+    const float v = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));
+    so[m] = v;
+    vmax = fmaxf(vmax, v);
+  }
+}
 
 // Shared memory plan (76.5 KB, two CTAs per SM):
 //   region 0 : sample tile with halo (phases 0-1)   -> power spectra [32][203] (phases 3-5)
 //   region 1 : FFT work [16 pairs][400] complex      -> staged log-mel rows [32][129] (phase 5)
+template <int NM>
 __global__ void __launch_bounds__(kLmThreads, 2)
 logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n_valid, long long n_total,
-              int n_frames, int n_mels, LogmelTables tb, float* __restrict__ out, float* __restrict__ gmax) {
+              int n_frames, LogmelTables tb, float* __restrict__ out, float* __restrict__ gmax) {
+  constexpr int n_mels = NM;
   extern __shared__ __align__(16) unsigned char lm_smem[];
   float* s_samples = reinterpret_cast<float*>(lm_smem);
   float* s_power = reinterpret_cast<float*>(lm_smem);
@@ -92,7 +111,7 @@ logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n
         a[n1].im = hw[n1] * fb[25 * n1];
       }
       lm::dft16(a);
-      lm::cpx* dst = s_work + p * kNfft + n2;
+      lm::cpx* dst = s_work + p * kPairStride + n2;
 #pragma unroll
       for (int k1 = 0; k1 < 16; k1 += 2) {
         dst[(k1 + 0) * 25] = lm::cmul(a[k1 + 0], lm::cpx{tw[k1 >> 1].x, tw[k1 >> 1].y});
@@ -109,7 +128,7 @@ logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n
   {
     static_assert(kPairs * 16 == kLmThreads, "one DFT-25 per thread");
     const int p = tid >> 4, k1 = tid & 15;
-    const lm::cpx* row = s_work + p * kNfft + k1 * 25;
+    const lm::cpx* row = s_work + p * kPairStride + k1 * 25;
     lm::cpx a[25];
 #pragma unroll
     for (int n2 = 0; n2 < 25; ++n2) a[n2] = row[n2];
@@ -139,15 +158,17 @@ logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n
   {
     const float* pw = s_power + lane * kPowStride;  // lane == frame within the tile
     float* so = s_out + lane * kOutStride;
-    for (int m = warp; m < n_mels; m += kLmThreads / 32) {
-      const int lo = __ldg(tb.mel_lo + m), cnt = __ldg(tb.mel_cnt + m);
-      const float* w = tb.mel_w + __ldg(tb.mel_off + m);
-      float acc = 0.0f;
-      for (int j = 0; j < cnt; ++j) acc = fmaf(__ldg(w + j), pw[lo + j], acc);
-      const float v = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));
-      so[m] = v;
-      if (f0 + lane < n_frames) vmax = fmaxf(vmax, v);
+    switch (warp) {
+      case 0: mel_for_warp<NM, 0>(pw, so, vmax); break;
+      case 1: mel_for_warp<NM, 1>(pw, so, vmax); break;
+      case 2: mel_for_warp<NM, 2>(pw, so, vmax); break;
+      case 3: mel_for_warp<NM, 3>(pw, so, vmax); break;
+      case 4: mel_for_warp<NM, 4>(pw, so, vmax); break;
+      case 5: mel_for_warp<NM, 5>(pw, so, vmax); break;
+      case 6: mel_for_warp<NM, 6>(pw, so, vmax); break;
+      default: mel_for_warp<NM, 7>(pw, so, vmax); break;
     }
+    if (f0 + lane >= n_frames) vmax = -INFINITY;  // frames past the end of the signal do not count
   }
   __syncthreads();
   const int valid_frames = min(kFrames, n_frames - f0);
@@ -223,21 +244,22 @@ __global__ void mel_window_kernel(const float* __restrict__ mel, const float* __
 
 // ---------------------------------------------------------------------------------------------- host
 static size_t logmel_smem_bytes() {
-  static_assert(sizeof(lm::cpx) * kPairs * kNfft >= sizeof(float) * kFrames * kOutStride, "staged rows fit the work area");
-  return sizeof(float) * kRegion0Floats + sizeof(lm::cpx) * kPairs * kNfft;
+  static_assert(sizeof(lm::cpx) * kPairs * kPairStride >= sizeof(float) * kFrames * kOutStride, "staged rows fit the work area");
+  return sizeof(float) * kRegion0Floats + sizeof(lm::cpx) * kPairs * kPairStride;
 }
 
 int init_logmel() {
   static bool done = false;
   if (done) return kOk;
-  B200W_CUDA_OK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_smem_bytes()));
+  B200W_CUDA_OK(cudaFuncSetAttribute(logmel_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_smem_bytes()));
+  B200W_CUDA_OK(cudaFuncSetAttribute(logmel_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_smem_bytes()));
   done = true;
   return kOk;
 }
 
 int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
-                  int n_mels, const float* hann, const float* tw400, const int* mel_lo, const int* mel_cnt,
-                  const int* mel_off, const float* mel_w, float* out_unclamped, float* gmax, cudaStream_t stream) {
+                  int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
+                  cudaStream_t stream) {
   B200W_CHECK_ARG(n_audio > 0 && n_valid > kNfft / 2 && n_total >= n_valid, "logmel: bad sizes");
   B200W_CHECK_ARG(n_mels == 80 || n_mels == 128, "logmel: n_mels must be 80 or 128, got %d", n_mels);
   const long long n_frames_ll = n_total / kHop;
@@ -248,11 +270,15 @@ int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long lo
   ProfScope prof_("logmel", stream);
   fill_f32_kernel<<<ceil_div(n_audio, 256), 256, 0, stream>>>(gmax, -INFINITY, n_audio);
   B200W_LAUNCH_OK();
-  LogmelTables tb{hann, reinterpret_cast<const float2*>(tw400), mel_lo, mel_cnt, mel_off, mel_w};
+  LogmelTables tb{hann, reinterpret_cast<const float2*>(tw400)};
   dim3 grid(ceil_div(n_frames, kFrames), n_audio);
   B200W_CHECK_ARG(n_audio <= 65535, "logmel: at most 65535 audios per call");
-  logmel_kernel<<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, n_mels, tb,
-                                                    out_unclamped, gmax);
+  if (n_mels == 80)
+    logmel_kernel<80><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, tb,
+                                                          out_unclamped, gmax);
+  else
+    logmel_kernel<128><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, tb,
+                                                           out_unclamped, gmax);
   B200W_LAUNCH_OK();
   count_launch(2);
   return kOk;
