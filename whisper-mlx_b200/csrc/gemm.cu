@@ -10,8 +10,8 @@
 //   warp 1   : MMA issuer     - one lane issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16), fp32
 //                               accumulators live in TMEM, double buffered across tiles
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue       - tcgen05.ld 32x32b -> bias / exact GELU / fp32 residual (or positional table)
-//                               -> bf16 or fp32 row-contiguous 16-byte global stores
+//   warps 4-11: epilogue      - tcgen05.ld 32x32b -> shared-memory transpose -> bias / GELU / fp32 residual (or
+//                               positional table) -> fully coalesced bf16 or fp32 global stores
 // A is addressed through a 3-D tensor map (k, row-in-batch, batch) so that the conv stem runs as an
 // implicit GEMM: with a (T+2, C) zero-padded NLC slab the im2col row of output t is the contiguous
 // 3*C span starting at padded row stride*t, i.e. just a tensor map with an overlapping row stride.
@@ -22,7 +22,8 @@ namespace b200w {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;            // 4 role warps + 8 epilogue warps
+constexpr int kEpiStageBytes = 8 * 32 * 33 * 4;  // per-warp padded 32x32 f32 transpose tiles
 
 template <int BN>
 struct GemmCfg {
@@ -31,7 +32,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiStageBytes;
 };
 
 template <int BN>
@@ -66,7 +67,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);
+      mbar_init(&tmem_empty_bar[i], 8);
     }
     fence_barrier_init();
   }
@@ -158,72 +159,70 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    // Epilogue: 8 warps.  Warp e reads TMEM lane quarter e % 4 (a hardware constraint: warp id % 4) and the 32-column
+    // chunks c = e / 4, e / 4 + 2, ...  A chunk arrives row-per-lane (tcgen05.ld 32x32b), is transposed through a
+    // padded per-warp shared-memory tile and leaves column-per-lane, so that every global access of a warp is one
+    // full 128-byte row segment (f32) or two 64-byte row segments (bf16): bias, residual and stores are coalesced.
+    const int e = warp - 4;
+    const int q = e & 3, hh = e >> 2;
+    float* stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + e * (32 * 33);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mt, nt, ks;
       decode_tile(tile, mt, nt, ks);
       const int b = mt / p.tiles_m_per_batch;
-      const int t = (mt - b * p.tiles_m_per_batch) * kBM + q * 32 + lane;
-      const bool row_ok = t < p.rows_per_batch;
-      const long long row = (long long)b * p.rows_per_batch + t;   // logical row (residual / positional index)
-      const long long orow = (long long)b * p.out_batch_rows + t;  // storage row
+      const int t0 = (mt - b * p.tiles_m_per_batch) * kBM + q * 32;  // first row (within the slab) of this warp
       const int n0 = nt * BN;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = hh; c < BN / 32; c += 2) {
         const int col = n0 + c * 32;
         if (col >= p.n_store) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32(t_base + c * 32, r);
         tmem_wait_ld();
-        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = __ldg(bp + j);
-            v[4 * j + 0] += bb.x;
-            v[4 * j + 1] += bb.y;
-            v[4 * j + 2] += bb.z;
-            v[4 * j + 3] += bb.w;
-          }
-        }
-        if (p.gelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (row_ok) {
-          if (p.resid != nullptr) {
-            const long long rr = (p.resid_mod > 0) ? (row % p.resid_mod) : row;
-            const float4* rp = reinterpret_cast<const float4*>(p.resid + rr * p.resid_ld + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 x = rp[j];
-              v[4 * j + 0] += x.x;
-              v[4 * j + 1] += x.y;
-              v[4 * j + 2] += x.z;
-              v[4 * j + 3] += x.w;
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int rows_here = min(32, p.rows_per_batch - t0);  // rows of this warp that exist (may be <= 0)
+        if (p.out_f32) {
+          const float bias_l = (p.bias != nullptr) ? __ldg(p.bias + col + lane) : 0.0f;
+          float* op = reinterpret_cast<float*>(p.out) + ks * p.split_stride + ((long long)b * p.out_batch_rows + t0) * p.ldc +
+                      col + lane;
+          const long long lrow0 = (long long)b * p.rows_per_batch + t0;
+#pragma unroll 4
+          for (int rr = 0; rr < rows_here; ++rr) {
+            float v = stage[rr * 33 + lane] + bias_l;
+            if (p.gelu) v = gelu_fast(v);
+            if (p.resid != nullptr) {
+              const long long lr = lrow0 + rr;
+              v += p.resid[((p.resid_mod > 0) ? (lr % p.resid_mod) : lr) * p.resid_ld + col + lane];
             }
+            op[(long long)rr * p.ldc] = v;
           }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ks * p.split_stride + orow * p.ldc + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldc + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              op[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                 pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+          // two rows per pass: lanes 0-15 the even row, lanes 16-31 the odd one, two adjacent columns per lane
+          const int l2 = (lane & 15) * 2, hi = lane >> 4;
+          float b0 = 0.0f, b1 = 0.0f;
+          if (p.bias != nullptr) {
+            b0 = __ldg(p.bias + col + l2);
+            b1 = __ldg(p.bias + col + l2 + 1);
+          }
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.out_batch_rows + t0) * p.ldc + col + l2;
+#pragma unroll 4
+          for (int rr = hi; rr < rows_here; rr += 2) {
+            float v0 = stage[rr * 33 + l2] + b0, v1 = stage[rr * 33 + l2 + 1] + b1;
+            if (p.gelu) {
+              v0 = gelu_fast(v0);
+              v1 = gelu_fast(v1);
             }
+            *reinterpret_cast<uint32_t*>(op + (long long)rr * p.ldc) = pack_bf16x2(v0, v1);
           }
         }
+        __syncwarp();
       }
       tcgen05_fence_before();
       __syncwarp();
