@@ -181,27 +181,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       for (int c = hh; c < BN / 32; c += 2) {
         const int col = n0 + c * 32;
         if (col >= p.n_store) break;  // warp-uniform
+        const int rows_here = min(32, p.rows_per_batch - t0);  // rows of this warp that exist (may be <= 0)
+        // residual rows first: 32 independent coalesced loads in flight while the accumulator is fetched and transposed
+        float rsd[32];
+        if (p.out_f32 && p.resid != nullptr) {
+          const long long lrow0 = (long long)b * p.rows_per_batch + t0;
+          long long ridx = (p.resid_mod > 0) ? (lrow0 % p.resid_mod) : lrow0;
+          const float* rp = p.resid + col + lane;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            rsd[rr] = (rr < rows_here) ? rp[ridx * p.resid_ld] : 0.0f;
+            if (++ridx == p.resid_mod) ridx = 0;
+          }
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) rsd[rr] = 0.0f;
+        }
         uint32_t r[32];
         tmem_ld_32x32(t_base + c * 32, r);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
         __syncwarp();
-        const int rows_here = min(32, p.rows_per_batch - t0);  // rows of this warp that exist (may be <= 0)
         if (p.out_f32) {
           const float bias_l = (p.bias != nullptr) ? __ldg(p.bias + col + lane) : 0.0f;
           float* op = reinterpret_cast<float*>(p.out) + ks * p.split_stride + ((long long)b * p.out_batch_rows + t0) * p.ldc +
                       col + lane;
-          const long long lrow0 = (long long)b * p.rows_per_batch + t0;
-#pragma unroll 4
-          for (int rr = 0; rr < rows_here; ++rr) {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
             float v = stage[rr * 33 + lane] + bias_l;
             if (p.gelu) v = gelu_fast(v);
-            if (p.resid != nullptr) {
-              const long long lr = lrow0 + rr;
-              v += p.resid[((p.resid_mod > 0) ? (lr % p.resid_mod) : lr) * p.resid_ld + col + lane];
-            }
-            op[(long long)rr * p.ldc] = v;
+            v += rsd[rr];
+            if (rr < rows_here) op[(long long)rr * p.ldc] = v;
           }
         } else {
           // two rows per pass: lanes 0-15 the even row, lanes 16-31 the odd one, two adjacent columns per lane
