@@ -126,35 +126,38 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, int T, int 
     __syncwarp();
 
     const int kv_valid = min(kBKV, T - j * kBKV);
-    // pass 1: row maximum
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int cb = 0; cb < 4; ++cb) {
+    // the whole 128-wide score row of this thread in registers: one pass over TMEM
+    float sc[128];
+    {
       uint32_t r[32];
-      tmem_ld_32x32(tmem_s + cb * 32, r);
-      tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float s = (cb * 32 + i < kv_valid) ? __uint_as_float(r[i]) : -INFINITY;
-        mx = fmaxf(mx, s);
+      for (int cb = 0; cb < 4; ++cb) {
+        tmem_ld_32x32(tmem_s + cb * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sc[cb * 32 + i] = __uint_as_float(r[i]);
       }
     }
+    if (kv_valid < kBKV) {  // only the last key block is ragged (block-uniform branch)
+#pragma unroll
+      for (int i = 0; i < 128; ++i)
+        if (i >= kv_valid) sc[i] = -INFINITY;
+    }
+    float mx = sc[0];
+#pragma unroll
+    for (int i = 1; i < 128; ++i) mx = fmaxf(mx, sc[i]);
     const float m_new = fmaxf(m_run, mx * c);
     const float alpha = fast_exp2(m_run - m_new);
     m_run = m_new;
-    // pass 2: probabilities -> swizzled bf16 A operand
+    // probabilities -> swizzled bf16 A operand (exp2(-inf) = 0 for the masked tail)
     float psum = 0.0f;
-#pragma unroll 1
+#pragma unroll
     for (int cb = 0; cb < 4; ++cb) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_s + cb * 32, r);
-      tmem_wait_ld();
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int c0 = cb * 32 + 2 * i;
-        float p0 = (c0 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(r[2 * i]), c, -m_new)) : 0.0f;
-        float p1 = (c0 + 1 < kv_valid) ? fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), c, -m_new)) : 0.0f;
+        const float p0 = fast_exp2(fmaf(sc[cb * 32 + 2 * i], c, -m_new));
+        const float p1 = fast_exp2(fmaf(sc[cb * 32 + 2 * i + 1], c, -m_new));
         psum += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
       }
