@@ -591,6 +591,26 @@ def case_decode_tiny():
     return out
 
 
+def case_decode_dual_stream():
+    """Batches of >= 16 windows decode as two half-batches on two streams; the result must not depend on it."""
+    from whisper_mlx_b200.decoding import DecodingOptions, DecodingTask
+
+    m = _product("tiny")
+    dims, _ = _oracle("tiny")
+    g = torch.Generator().manual_seed(3)
+    xa = _bf16(torch.randn(18, dims.n_audio_ctx, dims.n_audio_state, generator=g)).cuda()
+    outs = []
+    for n_streams in (1, 2, 2):
+        m.decode_streams = n_streams
+        task = DecodingTask(m, DecodingOptions(language="en", sample_len=48))
+        res = task.run_features(xa)
+        outs.append([(r.tokens, round(r.avg_logprob, 6), round(r.no_speech_prob, 9)) for r in res])
+    m.decode_streams = 2
+    assert len(outs[0]) == 18
+    assert outs[0] == outs[1] == outs[2], "two-stream decoding changed the result"
+    return {"tokens_first": outs[0][0][0][:8], "n": len(outs[0])}
+
+
 def case_transcribe_micro():
     """End-to-end `transcribe()` (log-mel -> encoder -> decode -> segments) vs the oracle, both modes."""
     from oracle import model as OM, transcribe as OT
@@ -632,5 +652,6 @@ CASES = {
     "encoder_tiny": case_encoder_tiny,
     "decoder_tiny": case_decoder_tiny,
     "decode_tiny": case_decode_tiny,
+    "decode_dual_stream": case_decode_dual_stream,
     "transcribe_micro": case_transcribe_micro,
 }

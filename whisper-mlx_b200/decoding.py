@@ -74,18 +74,26 @@ class DecodeSession:
     """Device-side decoding state for a batch of sequences sharing one set of cross K/V slots.
 
     Owns (through torch) the token buffer, per-sequence counters, the paged self-attention cache with its
-    block table, the cross K/V and the logits, and drives `b200w_decoder_step`.
+    block table, the cross K/V and the logits, and drives `b200w_decoder_step`.  A session is sized by
+    (n_audio, n_group, max_tokens); `Whisper.decode_session` keeps sessions alive between batches of the same
+    shape so that the buffers (30+ GB of cross K/V for 120 large-v3 windows) and the captured CUDA graphs are
+    reused: `load()` re-fills the cross K/V and resets the counters.
     """
 
-    def __init__(self, model, audio_features: torch.Tensor, n_group: int = 1, max_tokens: Optional[int] = None,
-                 cross_kv: Optional[torch.Tensor] = None):
+    def __init__(self, model, audio_features: Union[torch.Tensor, int], n_group: int = 1,
+                 max_tokens: Optional[int] = None, cross_kv: Optional[torch.Tensor] = None):
         self.model = model
         self.lib = model._lib
         dm = model.dims
         dev = model.device
-        if audio_features.ndim == 2:
-            audio_features = audio_features[None]
-        self.n_audio = audio_features.shape[0]
+        if isinstance(audio_features, int):
+            self.n_audio = audio_features
+            audio_features = None
+        else:
+            if audio_features.ndim == 2:
+                audio_features = audio_features[None]
+            self.n_audio = audio_features.shape[0]
+        self.n_group = n_group
         self.n_seq = self.n_audio * n_group
         B = self.n_seq
         max_tokens = min(max_tokens or dm.n_text_ctx, dm.n_text_ctx)
@@ -104,14 +112,19 @@ class DecodeSession:
         self.v_pages = torch.empty_like(self.k_pages)
         # page allocator: sequence b owns pages [b * max_pages, (b + 1) * max_pages)
         self.block_table = torch.arange(n_pages, dtype=torch.int32, device=dev).view(B, self.max_pages).contiguous()
-        self.cross = cross_kv if cross_kv is not None else model.cross_kv(audio_features.to(torch.bfloat16))
+        if cross_kv is not None:
+            self.cross = cross_kv
+        else:
+            self.cross = torch.empty((dm.n_text_layer, self.n_audio, dm.n_audio_ctx, 2 * d), dtype=torch.bfloat16, device=dev)
+            if audio_features is not None:
+                model.cross_kv(audio_features.to(torch.bfloat16), out=self.cross)
         self.cross_slot = (torch.arange(B, dtype=torch.int32, device=dev) // n_group).contiguous()
         ld = model.logits_ld
         self.logits = torch.empty((B, ld), dtype=torch.float32, device=dev)
         self.logits_aux = torch.empty((B, ld), dtype=torch.float32, device=dev)
         self.suppress_bits = torch.zeros((dm.n_vocab + 31) // 32, dtype=torch.int32, device=dev)
         self._ws: Dict[int, torch.Tensor] = {}
-        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graphs: Dict[bytes, Tuple[torch.cuda.CUDAGraph, int]] = {}  # keyed by the filter parameters baked in
         self._fp = _lib.FilterParams()
         self.state = _lib.DecodeState(
             B, _lib.ptr(self.tokens), self.tokens_ld, _lib.ptr(self.n_tokens), _lib.ptr(self.pos),
@@ -121,6 +134,13 @@ class DecodeSession:
             _lib.ptr(self.logits_aux), ld, _lib.ptr(self.suppress_bits))
 
     # -- setup -------------------------------------------------------------------------------------
+    def load(self, audio_features: torch.Tensor) -> None:
+        """Start a new batch in this session: project the encoder states into the (persistent) cross K/V."""
+        if audio_features.ndim == 2:
+            audio_features = audio_features[None]
+        assert audio_features.shape[0] == self.n_audio
+        self.model.cross_kv(audio_features.to(torch.bfloat16), out=self.cross)
+
     def set_tokens(self, tokens: torch.Tensor) -> None:
         """Load token histories (B, n); nothing is cached yet."""
         B, n = tokens.shape
@@ -168,17 +188,28 @@ class DecodeSession:
         """One single-token step + token selection, replayed from a CUDA graph after the first capture."""
         global GRAPH_KERNEL_LAUNCHES
         with torch.cuda.device(self.model.device):
-            if self._graph is None:
+            key = bytes(self._fp)
+            if key not in self._graphs:
                 self._workspace(1)
                 before = self.lib.b200w_launch_count()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._step(1, -1, True)
-                self._graph = g
-                self._graph_kernels = self.lib.b200w_launch_count() - before
-                GRAPH_KERNEL_LAUNCHES -= self._graph_kernels  # the capture itself launched nothing
-            self._graph.replay()
-            GRAPH_KERNEL_LAUNCHES += self._graph_kernels
+                # raw capture: torch.cuda.graph() would synchronise and empty the allocator cache
+                s = torch.cuda.Stream(device=self.model.device)
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    g.capture_begin()
+                    try:
+                        self._step(1, -1, True)
+                    finally:
+                        g.capture_end()
+                torch.cuda.current_stream().wait_stream(s)
+                n = self.lib.b200w_launch_count() - before
+                GRAPH_KERNEL_LAUNCHES -= n  # the capture itself launched nothing
+                self._graphs[key] = (g, n)
+            g, n = self._graphs[key]
+            self._graph_kernels = n
+            g.replay()
+            GRAPH_KERNEL_LAUNCHES += n
 
 
 class DecodingTask:
@@ -266,25 +297,59 @@ class DecodingTask:
         tk = self.tokenizer
         n_audio = audio_features.shape[0]
         n0 = len(self.initial_tokens)
-        sess = DecodeSession(self.model, audio_features, self.n_group, max_tokens=min(self.n_ctx, n0 + self.sample_len),
-                             cross_kv=cross_kv)
-        init = torch.tensor(self.initial_tokens, dtype=torch.int32).repeat(sess.n_seq, 1)
-        sess.set_tokens(init)
-        sess.set_filter(self._filter_params(sess), self._get_suppress_tokens())
+        max_tokens = min(self.n_ctx, n0 + self.sample_len)
+        model = self.model
+        # Two half-batches decoded on two streams: while one half streams its cross K/V (HBM-bound), the other
+        # half's small GEMM / LayerNorm / self-attention kernels (latency-bound) run beside it.
+        n_streams = 2 if (cross_kv is None and model.decode_streams >= 2 and n_audio >= 16) else 1
+        bounds = [(n_audio * i) // n_streams for i in range(n_streams + 1)]
+        sessions: List[DecodeSession] = []
+        for i in range(n_streams):
+            part = audio_features[bounds[i]: bounds[i + 1]]
+            if cross_kv is not None:
+                sess = DecodeSession(model, part, self.n_group, max_tokens=max_tokens, cross_kv=cross_kv)
+            else:
+                sess = model.decode_session(part.shape[0], self.n_group, max_tokens, slot=i)
+                sess.load(part)
+            init = torch.tensor(self.initial_tokens, dtype=torch.int32).repeat(sess.n_seq, 1)
+            sess.set_tokens(init)
+            sess.set_filter(self._filter_params(sess), self._get_suppress_tokens())
+            sessions.append(sess)
+        _lib.check(model._lib.b200w_set_option(b"cross_attention_ctas_per_sm", 4 if n_streams > 1 else 8))
 
-        sess.prompt_step(n0, self.sot_index)
+        for sess in sessions:
+            sess.prompt_step(n0, self.sot_index)
         steps = 1
         max_steps = min(self.sample_len, self.n_ctx + 1 - n0)
-        while steps < max_steps:
-            sess.sample_step()
-            steps += 1
-            if steps % poll_every == 0 and bool(sess.finished.all().item()):
-                break
+        if n_streams == 1:
+            sess = sessions[0]
+            while steps < max_steps:
+                sess.sample_step()
+                steps += 1
+                if steps % poll_every == 0 and bool(sess.finished.all().item()):
+                    break
+        else:
+            cur = torch.cuda.current_stream(model.device)
+            streams = model.side_streams(n_streams)
+            for st in streams:
+                st.wait_stream(cur)
+            while steps < max_steps:
+                for st, sess in zip(streams, sessions):
+                    with torch.cuda.stream(st):
+                        sess.sample_step()
+                steps += 1
+                if steps % poll_every == 0:
+                    for st in streams:
+                        st.synchronize()
+                    if all(bool(sess.finished.all().item()) for sess in sessions):
+                        break
+            for st in streams:
+                cur.wait_stream(st)
 
-        n_tok = int(sess.n_tokens[0].item())
-        tokens = sess.tokens[:, :n_tok].cpu().numpy()
-        sum_logprobs = sess.sum_logprob.cpu().numpy().astype(np.float64)
-        no_speech = sess.no_speech.cpu().numpy()[:: self.n_group]
+        n_tok = int(sessions[0].n_tokens[0].item())
+        tokens = torch.cat([sess.tokens[:, :n_tok] for sess in sessions], 0).cpu().numpy()
+        sum_logprobs = torch.cat([sess.sum_logprob for sess in sessions], 0).cpu().numpy().astype(np.float64)
+        no_speech = torch.cat([sess.no_speech for sess in sessions], 0).cpu().numpy()[:: self.n_group]
 
         tokens = tokens.reshape(n_audio, self.n_group, n_tok)
         sum_logprobs = sum_logprobs.reshape(n_audio, self.n_group)

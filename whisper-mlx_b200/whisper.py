@@ -65,6 +65,10 @@ class Whisper:
         self._lib = _lib.load()
         self._keep: List[torch.Tensor] = []
         self._handle = _lib.vp(0)
+        import os
+
+        # decode batches of >= 16 windows are split over this many concurrent streams (1 disables)
+        self.decode_streams = int(os.environ.get("B200W_DECODE_STREAMS", "2"))
         self._build(weights)
         # alignment heads default: all heads of the last half of the decoder layers (unused by ./run)
         all_heads = np.zeros((dims.n_text_layer, dims.n_text_head), dtype=bool)
@@ -212,12 +216,14 @@ class Whisper:
 
     encoder = embed_audio
 
-    def cross_kv(self, xa: torch.Tensor) -> torch.Tensor:
+    def cross_kv(self, xa: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Cross-attention K/V of every decoder layer: (L, W, 1500, 2d) bf16, rows [K | V]."""
         dm = self.dims
         Wn = xa.shape[0]
-        out = torch.empty((dm.n_text_layer, Wn, dm.n_audio_ctx, 2 * dm.n_text_state), dtype=torch.bfloat16,
-                          device=self.device)
+        shape = (dm.n_text_layer, Wn, dm.n_audio_ctx, 2 * dm.n_text_state)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.bfloat16, device=self.device)
+        assert tuple(out.shape) == shape and out.is_contiguous()
         xa = xa.contiguous()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.b200w_cross_kv(self._handle, _lib.ptr(xa), Wn, _lib.ptr(out), out.stride(0), 0,
@@ -225,6 +231,28 @@ class Whisper:
         return out
 
     # ------------------------------------------------------------------ decoder side
+    def side_streams(self, n: int):
+        streams = self.__dict__.setdefault("_side_streams", [])
+        while len(streams) < n:
+            streams.append(torch.cuda.Stream(device=self.device))
+        return streams[:n]
+
+    def decode_session(self, n_audio: int, n_group: int, max_tokens: int, slot: int = 0):
+        """A (cached) DecodeSession for batches of this shape; its buffers and CUDA graphs persist between calls.
+        `slot` distinguishes sessions of equal shape that are alive at the same time (two-stream decoding)."""
+        from .decoding import DecodeSession
+
+        key = (n_audio, n_group, max_tokens, slot)
+        cache = self.__dict__.setdefault("_sessions", {})
+        if key not in cache:
+            if len(cache) >= 6:  # bound the HBM held by idle sessions
+                cache.pop(next(iter(cache)))
+            cache[key] = DecodeSession(self, n_audio, n_group, max_tokens=max_tokens)
+        return cache[key]
+
+    def release_sessions(self) -> None:
+        self.__dict__.pop("_sessions", None)
+
     def logits(self, tokens: torch.Tensor, audio_features: torch.Tensor) -> torch.Tensor:
         """Teacher-forced logits (B, n, V) f32 for `tokens` (B, n) given encoder states.
 
