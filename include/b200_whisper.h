@@ -43,9 +43,6 @@ const char* b200w_version(void);
 const char* b200w_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py reports the delta). */
 unsigned long long b200w_launch_count(void);
-/* Tuning knobs.  "cross_attention_ctas_per_sm" (1..8, default 8): resident CTAs per SM of the persistent decode
- * cross-attention kernel; lower values leave room for a concurrent decode stream's small kernels. */
-int b200w_set_option(const char* name, int value);
 /* Per-kernel timing for benchmarks: between _begin and _end every eager launch of this library is bracketed
  * by CUDA events on its launch stream.  _end synchronises the device, writes a JSON object
  * {"<kernel>": {"launches": n, "total_ms": t}, ...} into `json` and returns the number of launches timed. */

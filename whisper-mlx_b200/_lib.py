@@ -70,7 +70,6 @@ SIGNATURES = {
     "b200w_version": (C.c_char_p, []),
     "b200w_last_error": (C.c_char_p, []),
     "b200w_launch_count": (u64, []),
-    "b200w_set_option": (i32, [C.c_char_p, i32]),
     "b200w_profile_begin": (i32, []),
     "b200w_profile_end": (i32, [C.c_char_p, sz]),
     "b200w_logmel": (i32, [vp, i32, i64, i64, i64, i32, C.POINTER(LogmelTables), vp, vp, vp]),

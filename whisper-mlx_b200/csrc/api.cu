@@ -283,16 +283,6 @@ const char* b200w_version(void) { return "b200-whisper 0.1 (abi 1, sm_100a)"; }
 const char* b200w_last_error(void) { return get_last_error(); }
 unsigned long long b200w_launch_count(void) { return g_launch_count; }
 
-int b200w_set_option(const char* name, int value) {
-  B200W_CHECK_ARG(name != nullptr, "set_option: null name");
-  if (strcmp(name, "cross_attention_ctas_per_sm") == 0) {
-    set_cross_attention_ctas_per_sm(value);
-    return kOk;
-  }
-  set_last_error("set_option: unknown option '%s'", name);
-  return kErrInvalidArgument;
-}
-
 int b200w_profile_begin(void) {
   for (auto& r : g_prof) {
     g_prof_pool.push_back(r.e0);

@@ -425,11 +425,8 @@ constexpr int kCrossThreads = 256;
 constexpr int kCrossWarps = kCrossThreads / 32;
 constexpr int kMaxCrossKeys = 1536;
 
-// Persistent: gridDim.x CTAs walk the (sequence, head, query) units.  The launcher caps the CTAs per SM so that a
-// decode step running on another stream (the other half of the batch) finds free thread / shared-memory slots
-// for its small GEMM / LayerNorm kernels while this HBM-bound kernel streams K and V.
 __global__ void __launch_bounds__(kCrossThreads)
-decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_seq, int n_q, int n_head,
+decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int n_head,
                                const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride, int T,
                                const int* __restrict__ slot, __nv_bfloat16* __restrict__ out,
                                const float* __restrict__ part, int n_split, long long split_stride,
@@ -443,9 +440,7 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_seq, i
   const int kg = lane >> 3;   // which of the warp's 4 concurrent keys
   const int d = n_head * kHd;
   const long long ld = 2ll * d;  // K | V interleaved per row
-  const int n_units = n_seq * n_head * n_q;
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-  const int h = unit % n_head, b = (unit / n_head) % n_seq, qi = unit / (n_head * n_seq);
+  const int h = blockIdx.x, b = blockIdx.y, qi = blockIdx.z;
   const __nv_bfloat16* kbase = cross_kv + (long long)slot[b] * seq_stride + h * kHd + sub * 8;
   const __nv_bfloat16* vbase = kbase + d;
 
@@ -567,12 +562,7 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_seq, i
     for (int w = 0; w < kCrossWarps; ++w) v += s_part[w][tid];
     out[((long long)b * n_q + qi) * d + h * kHd + tid] = __float2bfloat16(v / sum);
   }
-  __syncthreads();  // shared scratch is reused by the next unit
-  }
 }
-
-static int g_cross_ctas_per_sm = 8;
-void set_cross_attention_ctas_per_sm(int n) { g_cross_ctas_per_sm = n < 1 ? 1 : (n > 8 ? 8 : n); }
 
 int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, int n_head,
                                    const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
@@ -581,12 +571,10 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
   B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "cross_attention: bad sizes");
   B200W_CHECK_ARG(n_split > 0 ? (part && bias) : (q != nullptr), "cross_attention: missing query input");
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
-  const long long units = (long long)n_seq * n_head * n_q;
-  const long long cap = (long long)device_sm_count() * g_cross_ctas_per_sm;
-  const int grid = (int)(units < cap ? units : cap);
+  dim3 grid(n_head, n_seq, n_q);
   ProfScope prof_("decoder_cross_attention", stream);
-  decoder_cross_attention_kernel<<<grid, kCrossThreads, 0, stream>>>(q, n_seq, n_q, n_head, cross_kv, seq_stride, T,
-                                                                     slot, out, part, n_split, split_stride, bias);
+  decoder_cross_attention_kernel<<<grid, kCrossThreads, 0, stream>>>(q, n_q, n_head, cross_kv, seq_stride, T, slot,
+                                                                     out, part, n_split, split_stride, bias);
   B200W_LAUNCH_OK();
   count_launch();
   return kOk;

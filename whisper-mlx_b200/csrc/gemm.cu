@@ -30,9 +30,8 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // BN <= 64 serves the split-K decode GEMMs (<= a dozen K blocks per CTA): 4 stages keep the CTA small enough
-  // to co-reside with the capped cross-attention kernel of a concurrent decode stream
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 4);
+  // BN <= 64 serves the decode GEMMs: TMA latency (~1.2 us) over ~0.3 us per K block needs the deep ring
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiStageBytes;
 };

@@ -84,6 +84,4 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
                                    __nv_bfloat16* out, cudaStream_t stream, const float* part = nullptr,
                                    int n_split = 0, long long split_stride = 0, const float* bias = nullptr);
 
-void set_cross_attention_ctas_per_sm(int n);
-
 }  // namespace b200w

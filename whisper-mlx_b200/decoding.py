@@ -315,7 +315,6 @@ class DecodingTask:
             sess.set_tokens(init)
             sess.set_filter(self._filter_params(sess), self._get_suppress_tokens())
             sessions.append(sess)
-        _lib.check(model._lib.b200w_set_option(b"cross_attention_ctas_per_sm", 4 if n_streams > 1 else 8))
 
         for sess in sessions:
             sess.prompt_step(n0, self.sot_index)

@@ -68,7 +68,9 @@ class Whisper:
         import os
 
         # decode batches of >= 16 windows are split over this many concurrent streams (1 disables)
-        self.decode_streams = int(os.environ.get("B200W_DECODE_STREAMS", "2"))
+        # (measured on B200, r01: no gain yet -- the 60 K-register GEMM CTAs cannot co-reside with the cross-attention
+        # CTAs, so the two streams serialise; default off)
+        self.decode_streams = int(os.environ.get("B200W_DECODE_STREAMS", "1"))
         self._build(weights)
         # alignment heads default: all heads of the last half of the decoder layers (unused by ./run)
         all_heads = np.zeros((dims.n_text_layer, dims.n_text_head), dtype=bool)
