@@ -2,6 +2,7 @@
 // layer loops (reference: mlx_whisper/whisper.py::AudioEncoder.__call__, TextDecoder.__call__;
 // SURVEY.md A.2; call site /root/reference/run:3-6).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -56,6 +57,15 @@ ProfScope::ProfScope(const char* name, cudaStream_t s) : stream(s), slot(-1) {
 }
 ProfScope::~ProfScope() {
   if (slot >= 0) cudaEventRecord(g_prof[slot].e1, stream);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200W_PDL");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured on B200 (r01): 9.25 ms/step with PDL vs 7.67 without -> off
+  }
+  return v != 0;
 }
 
 int device_sm_count() {

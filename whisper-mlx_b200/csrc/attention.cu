@@ -63,6 +63,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, int T, int 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (T + kBKV - 1) / kBKV;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -84,6 +85,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, int T, int 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base + ((uint32_t)(warp * 32) << 16);
   const uint32_t tmem_o = tmem_s + 128;
+  pdl_wait();
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, kTileBytes);
@@ -241,8 +243,7 @@ int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n
   B200W_TRY(init_attention());
   dim3 grid(ceil_div(T, kBQ), n_head, n_batch);
   ProfScope prof_("encoder_attention", stream);
-  encoder_attention_kernel<<<grid, kEncThreads, kEncSmem, stream>>>(tm, T, d, out);
-  B200W_LAUNCH_OK();
+  B200W_CUDA_OK(launch_k(encoder_attention_kernel, grid, dim3(kEncThreads), kEncSmem, stream, tm, T, d, out));
   count_launch();
   return kOk;
 }
@@ -263,6 +264,8 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
   __shared__ float s_p[kSelfWarps][kMaxSelfKeys];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * kSelfWarps + warp;  // ((b * n_head) + h) * n_q + qi
+  pdl_launch_dependents();
+  pdl_wait();
   if (unit >= n_seq * n_head * n_q) return;
   const int qi = unit % n_q, h = (unit / n_q) % n_head, b = unit / (n_q * n_head);
   const int sub = lane & 7, kg = lane >> 3;
@@ -412,10 +415,9 @@ int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, 
   B200W_CHECK_ARG(max_pages_per_seq * page_size <= kMaxSelfKeys, "self_attention: context above %d", kMaxSelfKeys);
   const int units = n_seq * n_head * n_q;
   ProfScope prof_("decoder_self_attention", stream);
-  decoder_self_attention_kernel<<<ceil_div(units, kSelfWarps), kSelfThreads, 0, stream>>>(
-      qkv, n_seq, n_q, n_head, pos, k_pages, v_pages, block_table, max_pages_per_seq, page_size, out, part, n_split,
-      split_stride, bias);
-  B200W_LAUNCH_OK();
+  B200W_CUDA_OK(launch_k(decoder_self_attention_kernel, dim3(ceil_div(units, kSelfWarps)), dim3(kSelfThreads), 0, stream,
+                         qkv, n_seq, n_q, n_head, pos, k_pages, v_pages, block_table, max_pages_per_seq, page_size, out,
+                         part, n_split, split_stride, bias));
   count_launch();
   return kOk;
 }
@@ -441,6 +443,8 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   const int d = n_head * kHd;
   const long long ld = 2ll * d;  // K | V interleaved per row
   const int h = blockIdx.x, b = blockIdx.y, qi = blockIdx.z;
+  pdl_launch_dependents();
+  pdl_wait();
   const __nv_bfloat16* kbase = cross_kv + (long long)slot[b] * seq_stride + h * kHd + sub * 8;
   const __nv_bfloat16* vbase = kbase + d;
 
@@ -573,9 +577,8 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
   dim3 grid(n_head, n_seq, n_q);
   ProfScope prof_("decoder_cross_attention", stream);
-  decoder_cross_attention_kernel<<<grid, kCrossThreads, 0, stream>>>(q, n_q, n_head, cross_kv, seq_stride, T, slot,
-                                                                     out, part, n_split, split_stride, bias);
-  B200W_LAUNCH_OK();
+  B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head, cross_kv,
+                         seq_stride, T, slot, out, part, n_split, split_stride, bias));
   count_launch();
   return kOk;
 }

@@ -72,12 +72,39 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// Programmatic dependent launch: every kernel of the encoder / decoder chains is launched with the
+// programmatic-stream-serialization attribute, lets its successor be scheduled as soon as all of its own CTAs are
+// running (griddepcontrol.launch_dependents at the top) and waits for its predecessor's completion and memory flush
+// (griddepcontrol.wait) before it touches global memory.  The successor's launch latency and prologue (barrier
+// init, TMEM allocation, descriptor prefetch) then overlap the predecessor's tail.  Opt-in with B200W_PDL=1: on the
+// large-v3 decode step it measured slower (early-resident successors take SM resources from the predecessor).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 int device_sm_count();
 
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // small numeric helpers

@@ -18,6 +18,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                  int rows, int d, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   const int nvec = d >> 7;  // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
@@ -63,8 +65,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, int 
                      float* out_f32, cudaStream_t stream) {
   B200W_CHECK_ARG(rows > 0 && d > 0 && d % 128 == 0 && d <= 128 * kLnMaxVec, "layernorm: unsupported d=%d", d);
   ProfScope prof_("layernorm", stream);
-  layernorm_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, gamma, beta, rows, d, out_bf16, out_f32);
-  B200W_LAUNCH_OK();
+  B200W_CUDA_OK(launch_k(layernorm_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, stream, x, gamma, beta, rows, d, out_bf16,
+                         out_f32));
   count_launch();
   return kOk;
 }
@@ -80,6 +82,8 @@ resid_ln_small_kernel(float* __restrict__ x, const float* __restrict__ part, int
   __shared__ float s_red[2][10];
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const long long off = (long long)row * d + tid * 4;
+  pdl_launch_dependents();
+  pdl_wait();
   float4 v = *reinterpret_cast<const float4*>(x + off);
   if (n_split > 0) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + tid);
@@ -114,8 +118,8 @@ int launch_resid_ln_small(float* x, const float* part, int n_split, long long sp
   B200W_CHECK_ARG(rows > 0 && d % 128 == 0 && d <= 1280, "resid_ln: unsupported d=%d", d);
   B200W_CHECK_ARG(n_split == 0 || (part != nullptr && bias != nullptr), "resid_ln: partials without bias");
   ProfScope prof_("resid_ln", stream);
-  resid_ln_small_kernel<<<rows, d / 4, 0, stream>>>(x, part, n_split, split_stride, bias, gamma, beta, d, out_bf16);
-  B200W_LAUNCH_OK();
+  B200W_CUDA_OK(launch_k(resid_ln_small_kernel, dim3(rows), dim3(d / 4), 0, stream, x, part, n_split, split_stride, bias,
+                         gamma, beta, d, out_bf16));
   count_launch();
   return kOk;
 }
@@ -126,6 +130,8 @@ __global__ void embed_kernel(const int* __restrict__ tokens, int tokens_ld, cons
                              int d, int n_ctx, float* __restrict__ x) {
   const int r = blockIdx.x;  // b * n_q + qi
   const int b = r / n_q, qi = r - b * n_q;
+  pdl_launch_dependents();
+  pdl_wait();
   int p = pos[b] + qi;
   const int tok = tokens[(long long)b * tokens_ld + p];
   p = min(p, n_ctx - 1);
@@ -142,8 +148,8 @@ int launch_embed(const int* tokens, int tokens_ld, const int* pos, int n_seq, in
                  const __nv_bfloat16* pos_emb, int d, int n_ctx, float* x, cudaStream_t stream) {
   B200W_CHECK_ARG(n_seq > 0 && n_q > 0 && d % 2 == 0, "embed: bad sizes");
   ProfScope prof_("embed", stream);
-  embed_kernel<<<n_seq * n_q, 128, 0, stream>>>(tokens, tokens_ld, pos, n_q, tok_emb, pos_emb, d, n_ctx, x);
-  B200W_LAUNCH_OK();
+  B200W_CUDA_OK(launch_k(embed_kernel, dim3(n_seq * n_q), dim3(128), 0, stream, tokens, tokens_ld, pos, n_q, tok_emb, pos_emb,
+                         d, n_ctx, x));
   count_launch();
   return kOk;
 }
@@ -191,6 +197,8 @@ filter_argmax_kernel(const float* __restrict__ logits, const uint32_t* __restric
   __shared__ int s_last_ts_idx;
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = n_tokens[b];
   int* tok = tokens + (long long)b * fp.tokens_ld;
   const float* lg = logits + (long long)b * fp.logits_ld;
@@ -335,9 +343,8 @@ int launch_filter_argmax(const float* logits, const uint32_t* suppress_bits, int
                          float* sum_logprob, int* finished, int n_seq, const FilterParams& fp, cudaStream_t stream) {
   B200W_CHECK_ARG(n_seq > 0 && fp.n_vocab > 0 && fp.logits_ld >= fp.n_vocab, "filter_argmax: bad sizes");
   ProfScope prof_("filter_argmax", stream);
-  filter_argmax_kernel<<<n_seq, kFaThreads, 0, stream>>>(logits, suppress_bits, tokens, n_tokens, pos, sum_logprob,
-                                                         finished, fp);
-  B200W_LAUNCH_OK();
+  B200W_CUDA_OK(launch_k(filter_argmax_kernel, dim3(n_seq), dim3(kFaThreads), 0, stream, logits, suppress_bits, tokens,
+                         n_tokens, pos, sum_logprob, finished, fp));
   count_launch();
   return kOk;
 }
@@ -346,6 +353,8 @@ __global__ void __launch_bounds__(1024)
 no_speech_kernel(const float* __restrict__ logits, int logits_ld, int n_vocab, int no_speech, float* __restrict__ out) {
   __shared__ float s_red[32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   const float* lg = logits + (long long)b * logits_ld;
   float mx = -INFINITY;
   for (int v = tid; v < n_vocab; v += 1024) mx = fmaxf(mx, lg[v]);
@@ -370,8 +379,7 @@ no_speech_kernel(const float* __restrict__ logits, int logits_ld, int n_vocab, i
 int launch_no_speech(const float* logits, int logits_ld, int n_seq, int n_vocab, int no_speech, float* out,
                      cudaStream_t stream) {
   ProfScope prof_("no_speech", stream);
-  no_speech_kernel<<<n_seq, 1024, 0, stream>>>(logits, logits_ld, n_vocab, no_speech, out);
-  B200W_LAUNCH_OK();
+  B200W_CUDA_OK(launch_k(no_speech_kernel, dim3(n_seq), dim3(1024), 0, stream, logits, logits_ld, n_vocab, no_speech, out));
   count_launch();
   return kOk;
 }

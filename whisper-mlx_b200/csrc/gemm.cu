@@ -54,6 +54,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   const int tiles_m = p.n_batch * p.tiles_m_per_batch;
   const int num_tiles = tiles_m * p.tiles_n * p.split_k;
@@ -80,6 +81,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; operands and outputs are touched below
 
   // tile id -> (m tile, n tile): groups of group_m row tiles sweep all n tiles so the A rows of a group
   // stay L2-resident while W (small) is re-read from L2.
@@ -286,8 +288,7 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, GemmPara
   p.group_m = (int)(g < 8 ? 8 : (g > 148 ? 148 : g));
   const int grid = (int)(tiles < device_sm_count() ? tiles : device_sm_count());
   ProfScope prof_(p.tag ? p.tag : "gemm", stream);
-  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  B200W_LAUNCH_OK();
+  B200W_CUDA_OK(launch_k(gemm_bf16_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, p));
   count_launch();
   return kOk;
 }
