@@ -231,7 +231,8 @@ def run_product(args):
     line = None
     if rank == 0:
         roof = kernel_rooflines(model, peaks, min(n_windows, args.window_batch))
-        cpu = cpu_baseline(args, weights) if not args.no_cpu_baseline else None
+        # the CPU baseline is timed on rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1 for N > 1)
+        cpu = cpu_baseline(args, weights) if (not args.no_cpu_baseline and world == 1) else None
         dom = roof["cross_attention_decode"]
         line = {
             "metric": METRIC, "value": audio_s / dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

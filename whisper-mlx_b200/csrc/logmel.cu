@@ -52,42 +52,59 @@ __device__ __forceinline__ void mel_for_warp(const float* __restrict__ pw, float
   }
 }
 
-// Shared memory plan (76.5 KB, two CTAs per SM):
-//   region 0 : sample tile with halo (phases 0-1)   -> power spectra [32][203] (phases 3-5)
-//   region 1 : FFT work [16 pairs][400] complex      -> staged log-mel rows [32][129] (phase 5)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Persistent: 2 CTAs per SM walk the (audio, 32-frame tile) list; the next tile's samples stream into the second
+// sample buffer with cp.async while the current tile is transformed.
+// Shared memory plan (102.6 KB, two CTAs per SM):
+//   buffers 0/1 : sample tile with halo (phases 0-1) -> power spectra [32][203] of the same tile (phases 3-5);
+//                 the other buffer receives the next tile's samples meanwhile
+//   work        : FFT work [16 pairs][409] complex   -> staged log-mel rows [32][129] (phase 5)
 template <int NM>
 __global__ void __launch_bounds__(kLmThreads, 2)
 logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n_valid, long long n_total,
-              int n_frames, LogmelTables tb, float* __restrict__ out, float* __restrict__ gmax) {
+              int n_frames, int tiles_per_audio, int n_tiles, LogmelTables tb, float* __restrict__ out,
+              float* __restrict__ gmax) {
   constexpr int n_mels = NM;
   extern __shared__ __align__(16) unsigned char lm_smem[];
-  float* s_samples = reinterpret_cast<float*>(lm_smem);
-  float* s_power = reinterpret_cast<float*>(lm_smem);
-  lm::cpx* s_work = reinterpret_cast<lm::cpx*>(lm_smem + sizeof(float) * kRegion0Floats);
+  float* buf_cur = reinterpret_cast<float*>(lm_smem);
+  float* buf_nxt = buf_cur + kRegion0Floats;
+  lm::cpx* s_work = reinterpret_cast<lm::cpx*>(lm_smem + 2 * sizeof(float) * kRegion0Floats);
   float* s_out = reinterpret_cast<float*>(s_work);
   __shared__ float s_red[kLmThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int audio = blockIdx.y;
-  const int f0 = blockIdx.x * kFrames;
-  const float* x = pcm + (long long)audio * audio_stride;
-  const long long base = (long long)f0 * kHop - kNfft / 2;  // signal index of tile sample 0
+  const bool can_vec = ((audio_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
 
-  // ---- phase 0: stage samples ------------------------------------------------------------------
-  const bool interior = (base >= 0) && (base + kTile <= n_valid) && ((audio_stride & 3) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
-  if (interior) {
-    const float4* src = reinterpret_cast<const float4*>(x + base);  // base % 8 == 0
-    float4* dst = reinterpret_cast<float4*>(s_samples);
-#pragma unroll 2
-    for (int i = tid; i < kTile / 4; i += kLmThreads) dst[i] = __ldg(src + i);
-  } else {
-    for (int i = tid; i < kTile; i += kLmThreads) {
-      long long j = lm::reflect_index(base + i, n_valid, n_total);
-      s_samples[i] = (j >= 0) ? __ldg(x + j) : 0.0f;
+  // phase 0 of a tile: interior tiles stream in asynchronously, edge tiles (reflect / zero extension) synchronously
+  auto stage_tile = [&](float* dst, int t) {
+    const int a = t / tiles_per_audio;
+    const long long base = (long long)(t - a * tiles_per_audio) * kFrames * kHop - kNfft / 2;
+    const float* x = pcm + (long long)a * audio_stride;
+    if (can_vec && base >= 0 && base + kTile <= n_valid) {
+      for (int i = tid; i < kTile / 4; i += kLmThreads) cp_async16(dst + 4 * i, x + base + 4 * i);  // base % 8 == 0
+    } else {
+      for (int i = tid; i < kTile; i += kLmThreads) {
+        const long long j = lm::reflect_index(base + i, n_valid, n_total);
+        dst[i] = (j >= 0) ? __ldg(x + j) : 0.0f;
+      }
     }
-  }
-  __syncthreads();
+    cp_async_commit();
+  };
+
+  int tile = blockIdx.x;
+  if (tile < n_tiles) stage_tile(buf_cur, tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+  const int audio = tile / tiles_per_audio;
+  const int f0 = (tile - audio * tiles_per_audio) * kFrames;
+  float* s_samples = buf_cur;
+  float* s_power = buf_cur;
+  cp_async_wait_all();
+  __syncthreads();  // samples of this tile have landed; the previous tile's staged rows / power are no longer read
 
   // ---- phase 1: 25 column DFT-16 per pair + W400 twiddle ------------------------------------------
   // thread t < 250 owns column n2 = t % 25 for pairs t / 25 and t / 25 + 10: window and twiddles stay in registers
@@ -120,6 +137,7 @@ logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n
     }
   }
   __syncthreads();
+  if (tile + (int)gridDim.x < n_tiles) stage_tile(buf_nxt, tile + gridDim.x);  // overlaps phases 3-5
 
   // ---- phase 3: 16 row DFT-25 per pair; split the two real spectra in registers -------------------------
   // thread (p, k1) ends with Z[k1 + 16*k2], k2 < 25.  The conjugate partner Z[400 - k] of its bins k <= 200 lives
@@ -186,6 +204,10 @@ logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n
     for (int i = 1; i < kLmThreads / 32; ++i) m = fmaxf(m, s_red[i]);
     if (m > -INFINITY) atomic_max_float(gmax + audio, m);
   }
+  float* t = buf_cur;
+  buf_cur = buf_nxt;
+  buf_nxt = t;
+  }
 }
 
 __global__ void fill_f32_kernel(float* p, float v, int n) {
@@ -245,7 +267,7 @@ __global__ void mel_window_kernel(const float* __restrict__ mel, const float* __
 // ---------------------------------------------------------------------------------------------- host
 static size_t logmel_smem_bytes() {
   static_assert(sizeof(lm::cpx) * kPairs * kPairStride >= sizeof(float) * kFrames * kOutStride, "staged rows fit the work area");
-  return sizeof(float) * kRegion0Floats + sizeof(lm::cpx) * kPairs * kPairStride;
+  return 2 * sizeof(float) * kRegion0Floats + sizeof(lm::cpx) * kPairs * kPairStride;
 }
 
 int init_logmel() {
@@ -271,14 +293,17 @@ int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long lo
   fill_f32_kernel<<<ceil_div(n_audio, 256), 256, 0, stream>>>(gmax, -INFINITY, n_audio);
   B200W_LAUNCH_OK();
   LogmelTables tb{hann, reinterpret_cast<const float2*>(tw400)};
-  dim3 grid(ceil_div(n_frames, kFrames), n_audio);
-  B200W_CHECK_ARG(n_audio <= 65535, "logmel: at most 65535 audios per call");
+  const int tiles_per_audio = ceil_div(n_frames, kFrames);
+  const long long n_tiles_ll = (long long)tiles_per_audio * n_audio;
+  B200W_CHECK_ARG(n_tiles_ll < (1ll << 31), "logmel: too many tiles");
+  const int n_tiles = (int)n_tiles_ll;
+  const int grid = n_tiles < 2 * device_sm_count() ? n_tiles : 2 * device_sm_count();
   if (n_mels == 80)
-    logmel_kernel<80><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, tb,
-                                                          out_unclamped, gmax);
+    logmel_kernel<80><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, tiles_per_audio,
+                                                          n_tiles, tb, out_unclamped, gmax);
   else
-    logmel_kernel<128><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, tb,
-                                                           out_unclamped, gmax);
+    logmel_kernel<128><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, tiles_per_audio,
+                                                           n_tiles, tb, out_unclamped, gmax);
   B200W_LAUNCH_OK();
   count_launch(2);
   return kOk;
