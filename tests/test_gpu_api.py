@@ -1,0 +1,129 @@
+"""GPU tests of the reference-facing surface: CLI with the exact `./run` flags, weight formats, sampling,
+option validation.  Run with `pytest -m gpu` on a B200."""
+import json
+import os
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def micro_dir(tmp_path_factory, built_lib):
+    return synth.write_model(str(tmp_path_factory.mktemp("micro")), "micro", 0)
+
+
+def _write_wav(path, x):
+    pcm = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1), w.setsampwidth(2), w.setframerate(16000)
+        w.writeframes(pcm.tobytes())
+    return pcm.astype(np.float32) / 32768.0
+
+
+def test_cli_with_the_reference_flags(micro_dir, tmp_path, monkeypatch):
+    """`./run in out` == cli input -f txt --output-name out --model M --condition-on-previous-text False
+    --hallucination-silence-threshold 1 (/root/reference/run:3-6): writes out.txt, one line per segment."""
+    from whisper_mlx_b200 import transcribe
+    from whisper_mlx_b200.cli import main
+    from whisper_mlx_b200.load_models import load_model
+
+    wav = str(tmp_path / "in.wav")
+    x = _write_wav(wav, synth.long_audio(40.0, 5))
+    monkeypatch.chdir(tmp_path)
+    main([wav, "-f", "txt", "--output-name", "out", "--model", micro_dir, "--condition-on-previous-text", "False",
+          "--hallucination-silence-threshold", "1", "--verbose", "False", "--temperature-increment-on-fallback", "None",
+          "--language", "en"])
+    lines = open(tmp_path / "out.txt").read().splitlines()
+    ref = transcribe(x, model=load_model(micro_dir), condition_on_previous_text=False, temperature=0.0, language="en")
+    assert lines == [s["text"].strip() for s in ref["segments"]] and len(lines) >= 1
+
+
+def test_npz_and_fp16_weights_load_identically(micro_dir, tmp_path):
+    """The reference's other on-disk formats: weights.npz, fp16 storage."""
+    from safetensors.torch import load_file
+    from whisper_mlx_b200.load_models import load_model
+
+    w = load_file(os.path.join(micro_dir, "weights.safetensors"))
+    d2 = tmp_path / "npz"
+    d2.mkdir()
+    np.savez(str(d2 / "weights.npz"), **{k: v.float().numpy().astype(np.float16) for k, v in w.items()})
+    cfg = json.load(open(os.path.join(micro_dir, "config.json")))
+    json.dump(cfg, open(d2 / "config.json", "w"))
+    m1, m2 = load_model(micro_dir), load_model(str(d2))
+    mel = torch.randn(1, 3000, 80)
+    a, b = m1.embed_audio(mel).float(), m2.embed_audio(mel).float()
+    # bf16 weights are exactly representable in... not in fp16 in general: allow the fp16->bf16 re-rounding
+    assert (a - b).abs().max().item() <= 0.1 and (a - b).abs().mean().item() <= 5e-3
+
+
+def test_sampling_and_best_of(micro_dir):
+    """temperature > 0: Gumbel-max sampling on the device, best_of groups share the cross K/V slot, the ranker picks
+    the highest mean log-probability; seeded runs are reproducible and different seeds differ."""
+    from whisper_mlx_b200.decoding import DecodingOptions, DecodingTask
+    from whisper_mlx_b200.load_models import load_model
+
+    m = load_model(micro_dir)
+    g = torch.Generator().manual_seed(0)
+    xa = torch.randn(3, 1500, 128, generator=g).bfloat16().cuda()
+    greedy = DecodingTask(m, DecodingOptions(language="en", sample_len=16)).run_features(xa)
+    s1 = DecodingTask(m, DecodingOptions(language="en", sample_len=16, temperature=1.0, best_of=4, seed=1)).run_features(xa)
+    s1b = DecodingTask(m, DecodingOptions(language="en", sample_len=16, temperature=1.0, best_of=4, seed=1)).run_features(xa)
+    s2 = DecodingTask(m, DecodingOptions(language="en", sample_len=16, temperature=1.0, best_of=4, seed=2)).run_features(xa)
+    assert [r.tokens for r in s1] == [r.tokens for r in s1b]
+    assert [r.tokens for r in s1] != [r.tokens for r in s2]
+    assert any(a.tokens != b.tokens for a, b in zip(s1, greedy))
+    tb = 50364
+    for r in s1 + s2:
+        assert r.temperature == 1.0 and np.isfinite(r.avg_logprob) and r.avg_logprob < 0
+        assert len(r.tokens) >= 1 and tb <= r.tokens[0] <= tb + 50  # the timestamp grammar holds under sampling too
+    # near-zero temperature sampling reproduces greedy decoding
+    cold = DecodingTask(m, DecodingOptions(language="en", sample_len=16, temperature=1e-4, best_of=1, seed=3)).run_features(xa)
+    assert [r.tokens for r in cold] == [r.tokens for r in greedy]
+
+
+def test_temperature_fallback_in_transcribe(micro_dir):
+    """Random weights give avg_logprob << -1, so every temperature of the ladder is tried; the result carries the
+    last temperature, like the reference's decode_with_fallback."""
+    from whisper_mlx_b200 import transcribe
+    from whisper_mlx_b200.load_models import load_model
+
+    m = load_model(micro_dir)
+    r = transcribe(synth.white_noise(16000 * 20, 1), model=m, temperature=(0.0, 0.4, 0.8), best_of=2, language="en",
+                   condition_on_previous_text=False, sample_len=8)
+    assert len(r["segments"]) >= 1 and all(s["temperature"] == 0.8 for s in r["segments"])
+    r0 = transcribe(synth.white_noise(16000 * 20, 1), model=m, temperature=(0.0, 0.4, 0.8), best_of=2, language="en",
+                    condition_on_previous_text=False, sample_len=8, logprob_threshold=None, compression_ratio_threshold=None)
+    assert all(s["temperature"] == 0.0 for s in r0["segments"])
+
+
+def test_option_errors(micro_dir):
+    from whisper_mlx_b200 import transcribe
+    from whisper_mlx_b200.decoding import DecodingOptions, decode
+    from whisper_mlx_b200.load_models import load_model
+
+    m = load_model(micro_dir)
+    with pytest.raises(NotImplementedError):
+        decode(m, torch.zeros(3000, 80), DecodingOptions(language="en", beam_size=5))
+    with pytest.raises(AssertionError, match="incorrect audio shape"):
+        m.embed_audio(torch.zeros(1, 2999, 80))
+    with pytest.raises(NotImplementedError):
+        transcribe(synth.white_noise(16000, 0), model=m, word_timestamps=True)
+    with pytest.raises(ValueError):
+        transcribe(synth.white_noise(16000 * 40, 0), model=m, world_size=2, rank=0)  # sharding needs the fixed-window mode
+
+
+def test_prompt_conditioning_runs(micro_dir):
+    """condition_on_previous_text=True (the reference default): windows carry the previous tokens as a prompt."""
+    from whisper_mlx_b200 import transcribe
+    from whisper_mlx_b200.load_models import load_model
+
+    m = load_model(micro_dir)
+    r = transcribe(synth.long_audio(65.0, 2), model=m, temperature=0.0, language="en", sample_len=12,
+                   logprob_threshold=None, compression_ratio_threshold=None)
+    assert len(r["segments"]) >= 2 and r["segments"][-1]["seek"] > 0
