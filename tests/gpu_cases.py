@@ -591,6 +591,43 @@ def case_decode_tiny():
     return out
 
 
+def case_large_v3_parity():
+    """The named architecture (large-v3: 128 mel, d=1280, 20 heads, 32+32 layers, V=51866) with random-init weights:
+    encoder states, teacher-forced logits and argmax ids against the CPU oracle on one 30 s window."""
+    from oracle import audio as OA, model as OM
+    from oracle.tokens import TokenIds
+    from whisper_mlx_b200.whisper import ModelDimensions, Whisper
+
+    dims_d = synth.DIMS["large-v3"]
+    weights = dict(synth.random_weights(dims_d, 0, device="cuda"))
+    m = Whisper(ModelDimensions(**dims_d), weights)
+    w32 = {k: v.detach().to("cpu", torch.float32) for k, v in weights.items()}
+    del weights
+    dims = OM.ModelDimensions(**dims_d)
+    ids = TokenIds(dims.n_vocab)
+    tb = ids.timestamp_begin
+    torch.set_num_threads(os.cpu_count() or 1)
+    mel_t = torch.from_numpy(OA.log_mel_spectrogram(synth.make_audio("speech", 480000, 4), dims.n_mels))[None]
+    ref = OM.encoder_forward(w32, dims, mel_t, policy="bf16")
+    xa, xa32 = m.encode_slabs(m._mel_to_slabs(mel_t), want_f32=True)
+    d = (xa32.cpu() - ref).abs()
+    out = {"enc_max": d.max().item(), "enc_mean": d.mean().item(), "enc_ref_absmax": ref.abs().max().item()}
+    # 32 layers of bf16 storage: stated tolerance 8e-2 max-abs / 8e-3 mean-abs on unit-scale states
+    assert out["enc_max"] <= 8e-2 and out["enc_mean"] <= 8e-3, out
+    seq = list(ids.sot_sequence("en")) + [tb + 5, 300, 4000, tb + 80, tb + 80, 900, 901, tb + 200]
+    toks = torch.tensor([seq], dtype=torch.long)
+    ref_l, _ = OM.decoder_forward(w32, dims, toks, ref, policy="bf16")
+    got = m.logits(toks, ref.to(torch.bfloat16).cuda()).cpu()
+    out["logit_max"] = (got - ref_l).abs().max().item()
+    assert out["logit_max"] <= 8e-2, out
+    top2 = ref_l.topk(2, dim=-1).values
+    margin = top2[..., 0] - top2[..., 1]
+    same = got.argmax(-1) == ref_l.argmax(-1)
+    out["argmax_equal"] = f"{int(same.sum())}/{same.numel()}"
+    assert bool(same[margin > 2 * out["logit_max"]].all()), "argmax differs at a position with a safe margin"
+    return out
+
+
 def case_decode_dual_stream():
     """Batches of >= 16 windows decode as two half-batches on two streams; the result must not depend on it."""
     from whisper_mlx_b200.decoding import DecodingOptions, DecodingTask
@@ -652,6 +689,7 @@ CASES = {
     "encoder_tiny": case_encoder_tiny,
     "decoder_tiny": case_decoder_tiny,
     "decode_tiny": case_decode_tiny,
+    "large_v3_parity": case_large_v3_parity,
     "decode_dual_stream": case_decode_dual_stream,
     "transcribe_micro": case_transcribe_micro,
 }
