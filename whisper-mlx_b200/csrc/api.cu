@@ -68,6 +68,15 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+bool gemm2_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200W_GEMM2");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -148,6 +157,7 @@ static int gemm(const void* A, long long lda, int M, const void* W, int N, int K
   p.resid_mod = resid_mod;
   p.gelu = gelu ? 1 : 0;
   p.tag = tag;
+  if (gemm2_enabled() && gemm2_applicable(p)) return launch_gemm2(A, lda, W, p, stream);  // 2-CTA pairs, 256x256 tiles
   const int bn = gemm_block_n(1, M, N);
   CUtensorMap ta, tb;
   B200W_TRY(make_tmap_a(&ta, A, 1, M, K, lda, (long long)M * lda));
@@ -474,6 +484,7 @@ int b200w_model_create(const b200w_weights* w, b200w_model** out) {
                   "model_create: widths must be multiples of 128 up to 1280");
   B200W_CHECK_ARG(dm.n_audio_ctx == 1500 && dm.n_text_ctx <= 448, "model_create: unsupported context sizes");
   B200W_TRY(init_gemm());
+  B200W_TRY(init_gemm2());
   B200W_TRY(init_attention());
   B200W_TRY(init_logmel());
   b200w_model* m = new (std::nothrow) b200w_model();

@@ -49,6 +49,11 @@ struct GemmParams {
 
 int gemm_block_n(int n_batch, int rows_per_batch, int n_store);
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int block_n, cudaStream_t stream);
+// 2-CTA (cta_group::2) form for large plain GEMMs with N % 256 == 0 (gemm2.cu); B200W_GEMM2=0 disables it
+int init_gemm2();
+bool gemm2_enabled();
+bool gemm2_applicable(const GemmParams& p);
+int launch_gemm2(const void* A, long long lda, const void* W, GemmParams p, cudaStream_t stream);
 int make_tmap_w(CUtensorMap* out, const void* w, int N, int K, int block_n);
 int make_tmap_a(CUtensorMap* out, const void* a, int n_batch, int rows, int K, long long row_stride,
                 long long batch_stride);
