@@ -607,7 +607,9 @@ def case_large_v3_parity():
     ids = TokenIds(dims.n_vocab)
     tb = ids.timestamp_begin
     torch.set_num_threads(os.cpu_count() or 1)
-    mel_t = torch.from_numpy(OA.log_mel_spectrogram(synth.make_audio("speech", 480000, 4), dims.n_mels))[None]
+    # three windows: M = 4500 rows puts the bf16-output projections on the 2-CTA (cta_group::2) GEMM
+    mel_t = torch.from_numpy(np.stack([OA.log_mel_spectrogram(synth.make_audio(k, 480000, 4 + i), dims.n_mels)
+                                       for i, k in enumerate(("speech", "noise", "tones"))]))
     ref = OM.encoder_forward(w32, dims, mel_t, policy="bf16")
     xa, xa32 = m.encode_slabs(m._mel_to_slabs(mel_t), want_f32=True)
     d = (xa32.cpu() - ref).abs()
@@ -615,7 +617,7 @@ def case_large_v3_parity():
     # 32 layers of bf16 storage: stated tolerance 8e-2 max-abs / 8e-3 mean-abs on unit-scale states
     assert out["enc_max"] <= 8e-2 and out["enc_mean"] <= 8e-3, out
     seq = list(ids.sot_sequence("en")) + [tb + 5, 300, 4000, tb + 80, tb + 80, 900, 901, tb + 200]
-    toks = torch.tensor([seq], dtype=torch.long)
+    toks = torch.tensor([seq] * 3, dtype=torch.long)
     ref_l, _ = OM.decoder_forward(w32, dims, toks, ref, policy="bf16")
     got = m.logits(toks, ref.to(torch.bfloat16).cuda()).cpu()
     out["logit_max"] = (got - ref_l).abs().max().item()
