@@ -285,17 +285,17 @@ def case_decoder_attention():
     out = {}
     g = torch.Generator().manual_seed(0)
     H, d, ps = 6, 384, 16
-    # ---- self attention over pages: 3 sequences at different positions, n_q in {1, 3}
+    # ---- self attention over pages: sequences at different positions (one, two and four key sweeps), n_q in {1, 3}
     for n_q in (1, 3):
-        B, max_pages = 3, 8
-        pos = torch.tensor([0, 5, 37], dtype=torch.int32)
+        B, max_pages = 6, 28
+        pos = torch.tensor([0, 5, 37, 140, 227, 445], dtype=torch.int32)
         n_pages = B * max_pages
         perm = torch.randperm(n_pages, generator=g).to(torch.int32)  # scattered page table
         bt = perm.view(B, max_pages).contiguous()
         kp = torch.zeros(n_pages, ps, d, dtype=torch.bfloat16)
         vp = torch.zeros_like(kp)
-        hist_k = _bf16(torch.randn(B, 64, d, generator=g))
-        hist_v = _bf16(torch.randn(B, 64, d, generator=g))
+        hist_k = _bf16(torch.randn(B, 448, d, generator=g))
+        hist_v = _bf16(torch.randn(B, 448, d, generator=g))
         for b in range(B):
             for j in range(int(pos[b])):
                 pg = int(bt[b, j // ps])

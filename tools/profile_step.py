@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--eager", type=int, default=0)
     ap.add_argument("--skip-encoder", action="store_true")
     ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--trace", action="store_true", help="time every 16-step block up to 220 steps, then profile one eager step there")
     a = ap.parse_args()
 
     from bench import build_model
@@ -100,6 +101,26 @@ def main():
         torch.cuda.synchronize()
         out["decode_step_ms"] = e0.elapsed_time(e1) / a.steps
         out["graph_kernels_per_step"] = sess._graph_kernels
+        if a.trace:
+            from whisper_mlx_b200._lib import kernel_profile
+
+            done = 1 + a.steps
+            evs = [ev()]
+            evs[0].record()
+            marks = [done]
+            while done + 16 <= 220:
+                for _ in range(16):
+                    sess.sample_step()
+                done += 16
+                evs.append(ev())
+                evs[-1].record()
+                marks.append(done)
+            torch.cuda.synchronize()
+            out["step_ms_by_position"] = {str(marks[i + 1]): evs[i].elapsed_time(evs[i + 1]) / 16 for i in range(len(evs) - 1)}
+            with kernel_profile() as prof:
+                sess._step(1, -1, True)
+            out["eager_kernels_at_end"] = {k: {"launches": v["launches"], "ms": v["total_ms"],
+                                               "avg_us": v["total_ms"] / v["launches"] * 1e3} for k, v in prof.result.items()}
     print(json.dumps(out))
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     with open(os.path.join(REPO, "gpurun_out", "profile_step.json"), "w") as f:

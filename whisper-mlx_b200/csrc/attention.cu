@@ -249,24 +249,30 @@ int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n
 }
 
 // =============================================================================================== K7
-// One WARP per (sequence, head, query): no block-level barriers, 8 lanes per key row (16 B each), 4 rows per
-// load instruction, 4 instructions in flight -- the same access pattern as K8, sized for <= 448 cached keys.
-constexpr int kSelfWarps = 8;
+// One CTA of 4 warps per (sequence, head, query), the access pattern of K8: 8 lanes per key row (16 B each), 4 rows
+// per warp per load instruction, 8 loads in flight per thread (128 keys per CTA sweep), the first sweep of V issued
+// before the softmax barrier.  Sized for <= 448 cached keys.  (The first version used one warp per unit: at 220
+// cached keys it ran at 1.6 TB/s, latency-bound by its 2 KB in flight per warp.)
+constexpr int kSelfWarps = 4;
 constexpr int kSelfThreads = kSelfWarps * 32;
 constexpr int kMaxSelfKeys = 448;
+constexpr int kSelfUnroll = 8;
+constexpr int kSelfSweep = kSelfWarps * 4 * kSelfUnroll;  // keys per CTA sweep
 
 __global__ void __launch_bounds__(kSelfThreads)
 decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, int n_q, int n_head,
-                              const int* __restrict__ pos, __nv_bfloat16* __restrict__ k_pages,
-                              __nv_bfloat16* __restrict__ v_pages, const int* __restrict__ block_table, int max_pages,
-                              int page_size, __nv_bfloat16* __restrict__ out, const float* __restrict__ part,
-                              int n_split, long long split_stride, const float* __restrict__ bias) {
-  __shared__ float s_p[kSelfWarps][kMaxSelfKeys];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * kSelfWarps + warp;  // ((b * n_head) + h) * n_q + qi
+                              const int* __restrict__ pos, __nv_bfloat16* k_pages, __nv_bfloat16* v_pages,
+                              const int* __restrict__ block_table, int max_pages, int page_size,
+                              __nv_bfloat16* __restrict__ out, const float* __restrict__ part, int n_split,
+                              long long split_stride, const float* __restrict__ bias) {
+  __shared__ float s_p[kMaxSelfKeys];
+  __shared__ float s_red[kSelfWarps];
+  __shared__ float s_part[kSelfWarps][kHd];
+  __shared__ uint4 s_q[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int unit = blockIdx.x;  // ((b * n_head) + h) * n_q + qi
   pdl_launch_dependents();
   pdl_wait();
-  if (unit >= n_seq * n_head * n_q) return;
   const int qi = unit % n_q, h = (unit / n_q) % n_head, b = unit / (n_q * n_head);
   const int sub = lane & 7, kg = lane >> 3;
   const int d = n_head * kHd;
@@ -275,67 +281,80 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
   const long long my_row = ((long long)b * n_q + qi) * 3 * d;
   const bool split_mode = n_split > 0;  // qkv arrives as split-K fp32 partial slabs (+ bias), n_q == 1
   const int* bt = block_table + b * max_pages;
-  float* sp = s_p[warp];
   const float c = 0.125f * kLog2e;
+  const int pshift = __ffs(page_size) - 1;  // page_size is a power of two (checked by the launcher)
+  auto page_row = [&](int j) -> long long {
+    return ((long long)bt[j >> pshift] * page_size + (j & (page_size - 1))) * d + h * kHd + sub * 8;
+  };
 
   // ---- this token's q (registers, 8 dims per lane) and k / v rows (appended to the paged cache) ----
   float qv[8];
   {
-    const int j = p0 + qi;
-    const long long dst = ((long long)bt[j / page_size] * page_size + j % page_size) * d + h * kHd + sub * 8;
+    uint4 qu;
     if (split_mode) {
-      // lanes 0-7 reduce q, 8-15 k, 16-23 v (8 consecutive dims each); q is then broadcast to the whole warp
-      float v8[8];
-      const int which = kg < 3 ? kg : 0;
-      const long long col = (long long)which * d + h * kHd + sub * 8;
+      // warp 0: lanes 0-7 reduce q, 8-15 k, 16-23 v (8 consecutive dims each); q goes to the CTA through s_q
+      if (warp == 0 && kg < 3) {
+        float v8[8];
+        const long long col = (long long)kg * d + h * kHd + sub * 8;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v8[i] = bias[col + i];
-      for (int sidx = 0; sidx < n_split; ++sidx) {
-        const float* pp = part + sidx * split_stride + (long long)b * 3 * d + col;
-        const float4 a0 = *reinterpret_cast<const float4*>(pp), a1 = *reinterpret_cast<const float4*>(pp + 4);
-        v8[0] += a0.x; v8[1] += a0.y; v8[2] += a0.z; v8[3] += a0.w;
-        v8[4] += a1.x; v8[5] += a1.y; v8[6] += a1.z; v8[7] += a1.w;
+        for (int i = 0; i < 8; ++i) v8[i] = bias[col + i];
+        for (int sidx = 0; sidx < n_split; ++sidx) {
+          const float* pp = part + sidx * split_stride + (long long)b * 3 * d + col;
+          const float4 a0 = *reinterpret_cast<const float4*>(pp), a1 = *reinterpret_cast<const float4*>(pp + 4);
+          v8[0] += a0.x; v8[1] += a0.y; v8[2] += a0.z; v8[3] += a0.w;
+          v8[4] += a1.x; v8[5] += a1.y; v8[6] += a1.z; v8[7] += a1.w;
+        }
+        const uint4 packed = make_uint4(pack_bf16x2(v8[0], v8[1]), pack_bf16x2(v8[2], v8[3]), pack_bf16x2(v8[4], v8[5]),
+                                        pack_bf16x2(v8[6], v8[7]));
+        const long long dst = page_row(p0);
+        if (kg == 0) s_q[sub] = packed;  // q rounded to bf16 like the GEMM epilogue would have
+        if (kg == 1) *reinterpret_cast<uint4*>(k_pages + dst) = packed;
+        if (kg == 2) *reinterpret_cast<uint4*>(v_pages + dst) = packed;
       }
-      const uint4 packed = make_uint4(pack_bf16x2(v8[0], v8[1]), pack_bf16x2(v8[2], v8[3]), pack_bf16x2(v8[4], v8[5]),
-                                      pack_bf16x2(v8[6], v8[7]));
-      if (kg == 1) *reinterpret_cast<uint4*>(k_pages + dst) = packed;
-      if (kg == 2) *reinterpret_cast<uint4*>(v_pages + dst) = packed;
-      // q (rounded to bf16 like the GEMM epilogue would have) from lane `sub` of group 0
-      uint32_t w0 = __shfl_sync(0xffffffffu, packed.x, sub), w1 = __shfl_sync(0xffffffffu, packed.y, sub);
-      uint32_t w2 = __shfl_sync(0xffffffffu, packed.z, sub), w3 = __shfl_sync(0xffffffffu, packed.w, sub);
-      const float2 a0 = unpack_bf16x2(w0), a1 = unpack_bf16x2(w1), a2 = unpack_bf16x2(w2), a3 = unpack_bf16x2(w3);
-      qv[0] = a0.x * c; qv[1] = a0.y * c; qv[2] = a1.x * c; qv[3] = a1.y * c;
-      qv[4] = a2.x * c; qv[5] = a2.y * c; qv[6] = a3.x * c; qv[7] = a3.y * c;
-      __syncwarp();
+      __syncthreads();  // s_q and this CTA's appended rows are visible to all four warps
+      qu = s_q[sub];
     } else {
-      const uint4 u = *reinterpret_cast<const uint4*>(qkv + my_row + h * kHd + sub * 8);
-      const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-      qv[0] = a0.x * c; qv[1] = a0.y * c; qv[2] = a1.x * c; qv[3] = a1.y * c;
-      qv[4] = a2.x * c; qv[5] = a2.y * c; qv[6] = a3.x * c; qv[7] = a3.y * c;
-      if (kg == 1) *reinterpret_cast<uint4*>(k_pages + dst) = *reinterpret_cast<const uint4*>(qkv + my_row + d + h * kHd + sub * 8);
-      if (kg == 2) *reinterpret_cast<uint4*>(v_pages + dst) = *reinterpret_cast<const uint4*>(qkv + my_row + 2 * d + h * kHd + sub * 8);
+      qu = *reinterpret_cast<const uint4*>(qkv + my_row + h * kHd + sub * 8);
+      if (warp == 0 && (kg == 1 || kg == 2)) {
+        const long long dst = page_row(p0 + qi);
+        *reinterpret_cast<uint4*>((kg == 1 ? k_pages : v_pages) + dst) =
+            *reinterpret_cast<const uint4*>(qkv + my_row + (long long)kg * d + h * kHd + sub * 8);
+      }
     }
+    const float2 a0 = unpack_bf16x2(qu.x), a1 = unpack_bf16x2(qu.y), a2 = unpack_bf16x2(qu.z), a3 = unpack_bf16x2(qu.w);
+    qv[0] = a0.x * c; qv[1] = a0.y * c; qv[2] = a1.x * c; qv[3] = a1.y * c;
+    qv[4] = a2.x * c; qv[5] = a2.y * c; qv[6] = a3.x * c; qv[7] = a3.y * c;
   }
-  // rows of position j: cached pages for j < p0 (and, in split mode, the row this warp just appended);
-  // this step's qkv rows otherwise (other warps append those concurrently)
-  auto row_ptr = [&](int j, int which) -> const __nv_bfloat16* {
-    if (j >= p0 && !split_mode) return qkv + ((long long)b * n_q + (j - p0)) * 3 * d + (long long)which * d + h * kHd + sub * 8;
-    const __nv_bfloat16* base = which == 1 ? k_pages : v_pages;
-    return base + ((long long)bt[j / page_size] * page_size + j % page_size) * d + h * kHd + sub * 8;
+  // rows of position j: cached pages for j < p0 (and, in split mode, the row this CTA just appended); this step's
+  // qkv rows otherwise (other CTAs append those concurrently).  Branch-free on purpose: positions past the end are
+  // clamped to the last key (their values are masked by the callers), the page ids of a sweep are fetched first and
+  // the row loads follow back to back -- with per-load branches the compiler put every row's unpacking between the
+  // loads and the sweep ran one load at a time.
+  const long long qkv_seq = (long long)b * n_q * 3 * d + h * kHd + sub * 8;
+  auto load_rows = [&](uint4 (&u)[kSelfUnroll], int j0, int which) {
+    int jc[kSelfUnroll], pg[kSelfUnroll];
+#pragma unroll
+    for (int i = 0; i < kSelfUnroll; ++i) {
+      jc[i] = min(j0 + kg + i * (kSelfWarps * 4), n_keys - 1);
+      pg[i] = bt[jc[i] >> pshift];
+    }
+    __nv_bfloat16* pages = which == 1 ? k_pages : v_pages;
+#pragma unroll
+    for (int i = 0; i < kSelfUnroll; ++i) {
+      const bool fresh = jc[i] >= p0 && !split_mode;
+      const __nv_bfloat16* base = fresh ? qkv : pages;
+      const long long off = fresh ? qkv_seq + (long long)(jc[i] - p0) * 3 * d + (long long)which * d
+                                  : ((long long)pg[i] * page_size + (jc[i] & (page_size - 1))) * d + h * kHd + sub * 8;
+      u[i] = *reinterpret_cast<const uint4*>(base + off);
+    }
   };
 
   // ---- scores ----
   float mx = -INFINITY;
-  for (int j0 = 0; j0 < n_keys; j0 += 16) {  // warp-uniform trip count: the shuffles below need every lane
-    uint4 u[4];
+  auto score_rows = [&](const uint4 (&u)[kSelfUnroll], int j0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = j0 + kg + 4 * i;
-      u[i] = (j < n_keys) ? *reinterpret_cast<const uint4*>(row_ptr(j, 1)) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = j0 + kg + 4 * i;
+    for (int i = 0; i < kSelfUnroll; ++i) {
+      const int j = j0 + kg + i * (kSelfWarps * 4);
       const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z), a3 = unpack_bf16x2(u[i].w);
       float sc = a0.x * qv[0];
       sc = fmaf(a0.y, qv[1], sc);
@@ -349,48 +368,64 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
       sc += __shfl_xor_sync(0xffffffffu, sc, 2);
       sc += __shfl_xor_sync(0xffffffffu, sc, 4);
       if (j < n_keys) {
-        if (sub == 0) sp[j] = sc;
+        if (sub == 0) s_p[j] = sc;
         mx = fmaxf(mx, sc);
       }
     }
+  };
+  for (int j0 = warp * 4; j0 < n_keys; j0 += kSelfSweep) {  // warp-uniform trip count: the shuffles need every lane
+    uint4 u[kSelfUnroll];
+    load_rows(u, j0, 1);
+    score_rows(u, j0);
   }
+  // the first sweep of V does not depend on the probabilities: put it in flight across the softmax barriers
+  uint4 v0[kSelfUnroll];
+  load_rows(v0, warp * 4, 2);
   mx = warp_max(mx);
-  __syncwarp();
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int i = 1; i < kSelfWarps; ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
   float sum = 0.0f;
-  for (int j = lane; j < n_keys; j += 32) {
-    const float p = fast_exp2(sp[j] - mx);
+  for (int j = tid; j < n_keys; j += kSelfThreads) {
+    const float p = fast_exp2(s_p[j] - mx);
     sum += p;
-    sp[j] = __bfloat162float(__float2bfloat16(p));  // bf16 probabilities, as in the tensor-core path
+    s_p[j] = __bfloat162float(__float2bfloat16(p));  // bf16 probabilities, as in the tensor-core path
   }
   sum = warp_sum(sum);
-  __syncwarp();
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kSelfWarps; ++i) sum += s_red[i];
 
   // ---- output ----
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-  for (int j0 = 0; j0 < n_keys; j0 += 16) {
-    uint4 u[4];
-    float p[4];
+  auto accumulate = [&](const uint4 (&u)[kSelfUnroll], int j0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int j = j0 + kg + 4 * i;
-      const bool ok = j < n_keys;
-      u[i] = ok ? *reinterpret_cast<const uint4*>(row_ptr(j, 2)) : make_uint4(0, 0, 0, 0);
-      p[i] = ok ? sp[j] : 0.0f;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kSelfUnroll; ++i) {
+      const int j = j0 + kg + i * (kSelfWarps * 4);
+      const float p = (j < n_keys) ? s_p[j] : 0.0f;
       const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z), a3 = unpack_bf16x2(u[i].w);
-      acc[0] = fmaf(p[i], a0.x, acc[0]);
-      acc[1] = fmaf(p[i], a0.y, acc[1]);
-      acc[2] = fmaf(p[i], a1.x, acc[2]);
-      acc[3] = fmaf(p[i], a1.y, acc[3]);
-      acc[4] = fmaf(p[i], a2.x, acc[4]);
-      acc[5] = fmaf(p[i], a2.y, acc[5]);
-      acc[6] = fmaf(p[i], a3.x, acc[6]);
-      acc[7] = fmaf(p[i], a3.y, acc[7]);
+      acc[0] = fmaf(p, a0.x, acc[0]);
+      acc[1] = fmaf(p, a0.y, acc[1]);
+      acc[2] = fmaf(p, a1.x, acc[2]);
+      acc[3] = fmaf(p, a1.y, acc[3]);
+      acc[4] = fmaf(p, a2.x, acc[4]);
+      acc[5] = fmaf(p, a2.y, acc[5]);
+      acc[6] = fmaf(p, a3.x, acc[6]);
+      acc[7] = fmaf(p, a3.y, acc[7]);
     }
+  };
+  accumulate(v0, warp * 4);
+  for (int j0 = warp * 4 + kSelfSweep; j0 < n_keys; j0 += kSelfSweep) {
+    uint4 u[kSelfUnroll];
+    load_rows(u, j0, 2);
+    accumulate(u, j0);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -398,10 +433,15 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
     acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
   }
   if (kg == 0) {
-    const float inv = 1.0f / sum;
-    *reinterpret_cast<uint4*>(out + ((long long)b * n_q + qi) * d + h * kHd + sub * 8) =
-        make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
-                   pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_part[warp][sub * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < kHd) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kSelfWarps; ++w) v += s_part[w][tid];
+    out[((long long)b * n_q + qi) * d + h * kHd + tid] = __float2bfloat16(v / sum);
   }
 }
 
@@ -413,9 +453,10 @@ int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, 
   B200W_CHECK_ARG(n_split > 0 || qkv, "self_attention: null qkv");
   B200W_CHECK_ARG(n_seq > 0 && n_q > 0 && (long long)n_seq * n_q * n_head < (1ll << 30), "self_attention: bad sizes");
   B200W_CHECK_ARG(max_pages_per_seq * page_size <= kMaxSelfKeys, "self_attention: context above %d", kMaxSelfKeys);
+  B200W_CHECK_ARG(page_size > 0 && (page_size & (page_size - 1)) == 0, "self_attention: page_size must be a power of two");
   const int units = n_seq * n_head * n_q;
   ProfScope prof_("decoder_self_attention", stream);
-  B200W_CUDA_OK(launch_k(decoder_self_attention_kernel, dim3(ceil_div(units, kSelfWarps)), dim3(kSelfThreads), 0, stream,
+  B200W_CUDA_OK(launch_k(decoder_self_attention_kernel, dim3(units), dim3(kSelfThreads), 0, stream,
                          qkv, n_seq, n_q, n_head, pos, k_pages, v_pages, block_table, max_pages_per_seq, page_size, out,
                          part, n_split, split_stride, bias));
   count_launch();
