@@ -66,6 +66,11 @@ typedef struct {
  * gmax[a] the maximum over signal a (the clamp reference of the reference's `log_spec.max() - 8`). */
 int b200w_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
                  int n_mels, const b200w_logmel_tables* tables, float* out_unclamped, float* gmax, void* stream);
+/* Same, from s16le PCM (the stream `load_audio` asks ffmpeg for, UPSTREAM audio.py):
+ * the `/ 32768.0` of load_audio is applied while the samples are staged, so results are bit-identical to
+ * b200w_logmel on the converted floats.  audio_stride in samples. */
+int b200w_logmel_pcm16(const int16_t* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
+                       int n_mels, const b200w_logmel_tables* tables, float* out_unclamped, float* gmax, void* stream);
 /* In place: x <- (max(x, gmax[a] - 8) + 4) / 4 for the per_audio values of each signal. */
 int b200w_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, void* stream);
 /* Window gather fused with the clamp/scale and the bf16 cast that feeds the conv stem.  Replaces

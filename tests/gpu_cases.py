@@ -113,6 +113,26 @@ def case_logmel_shapes():
     return out
 
 
+def case_logmel_pcm16():
+    """int16 PCM ingestion (the s16le stream load_audio decodes): bit-identical to the f32 path on pcm / 32768, for
+    interior tiles (vector loads), edge tiles (reflect, ragged length, padding) and a batch with a row stride."""
+    from whisper_mlx_b200.audio import log_mel_spectrogram
+
+    out = {}
+    for n, pad, n_mels in ((480000, 0, 80), (16000 * 7 + 123, 480000, 128), (401, 0, 80)):
+        pcm = np.clip(np.round(synth.make_audio("speech", n, n) * 32768.0), -32768, 32767).astype(np.int16)
+        a = log_mel_spectrogram(pcm, n_mels=n_mels, padding=pad)
+        b = log_mel_spectrogram(pcm.astype(np.float32) / 32768.0, n_mels=n_mels, padding=pad)
+        out[f"n{n}_p{pad}_{n_mels}"] = float((a - b).abs().max().item())
+        assert torch.equal(a, b), (n, pad, n_mels)
+    pcm = np.clip(np.round(np.stack([synth.white_noise(48000, 1), synth.make_audio("tones", 48000, 3)]) * 32768.0), -32768, 32767).astype(np.int16)
+    a = log_mel_spectrogram(torch.from_numpy(pcm).cuda(), n_mels=128)
+    b = log_mel_spectrogram(pcm.astype(np.float32) / 32768.0, n_mels=128)
+    assert torch.equal(a, b)
+    out["batched"] = 0.0
+    return out
+
+
 # ------------------------------------------------------------------------------------------ K5 GEMM
 def _gemm_ref(a, w, bias, gelu, resid):
     y = a.float() @ w.float().T
@@ -687,6 +707,7 @@ CASES = {
     "encoder_attention": case_encoder_attention,
     "decoder_attention": case_decoder_attention,
     "splitk_decode_ops": case_splitk_decode_ops,
+    "logmel_pcm16": case_logmel_pcm16,
     "filter_argmax": case_filter_argmax,
     "encoder_tiny": case_encoder_tiny,
     "decoder_tiny": case_decoder_tiny,

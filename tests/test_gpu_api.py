@@ -127,3 +127,54 @@ def test_prompt_conditioning_runs(micro_dir):
     r = transcribe(synth.long_audio(65.0, 2), model=m, temperature=0.0, language="en", sample_len=12,
                    logprob_threshold=None, compression_ratio_threshold=None)
     assert len(r["segments"]) >= 2 and r["segments"][-1]["seek"] > 0
+
+
+def test_daemon_tool_transcribes(micro_dir, tmp_path):
+    """The reference's plugin API (Tool.execute(**arguments) -> JSON string) over the transcription path."""
+    from whisper_mlx_b200 import transcribe
+    from whisper_mlx_b200.load_models import load_model
+    from whisper_mlx_b200.tool import TOOL
+
+    wav = str(tmp_path / "in.wav")
+    x = _write_wav(wav, synth.long_audio(40.0, 5))
+    r = json.loads(TOOL.execute(file_path=wav, language="en", model=micro_dir))
+    assert r["status"] == "success", r
+    ref = transcribe(x, model=load_model(micro_dir), condition_on_previous_text=False, language="en")
+    assert r["text"] == ref["text"].strip() and r["segment_count"] == len(ref["segments"]) and r["language"] == "en"
+    assert [s["text"] for s in r["segments"]] == [s["text"].strip() for s in ref["segments"]]
+
+
+def test_mlx_quantised_checkpoint_loads(micro_dir, tmp_path):
+    """A 4-bit MLX-quantised checkpoint (`quantization` in config.json, uint32 weight + scales + biases per Linear /
+    Embedding) runs and equals the model built from the same weights expanded by hand."""
+    from safetensors.torch import load_file, save_file
+    from tests.test_host_logic import _mlx_quantize
+    from whisper_mlx_b200.load_models import load_model
+
+    w = load_file(os.path.join(micro_dir, "weights.safetensors"))
+    cfg = json.load(open(os.path.join(micro_dir, "config.json")))
+    qdir, ddir = tmp_path / "q4", tmp_path / "dense"
+    qdir.mkdir(), ddir.mkdir()
+    wq, wd = {}, {}
+    for k, v in w.items():
+        quantise = k.endswith(".weight") and v.ndim == 2 and (".attn." in k or ".cross_attn." in k or ".mlp1." in k or ".mlp2." in k or k == "decoder.token_embedding.weight")
+        if quantise:
+            words, scales, biases, dense = _mlx_quantize(v.float(), 64, 4)
+            base = k[: -len(".weight")]
+            wq[k], wq[base + ".scales"], wq[base + ".biases"] = words.view(torch.int32), scales.half(), biases.half()
+            wd[k] = (_dequant_like(words, scales.half(), biases.half())).to(torch.bfloat16)
+        else:
+            wq[k], wd[k] = v.contiguous(), v.contiguous()
+    save_file(wq, str(qdir / "weights.safetensors"))
+    save_file(wd, str(ddir / "weights.safetensors"))
+    json.dump({**cfg, "quantization": {"group_size": 64, "bits": 4}}, open(qdir / "config.json", "w"))
+    json.dump(cfg, open(ddir / "config.json", "w"))
+    mq, md = load_model(str(qdir)), load_model(str(ddir))
+    mel = torch.randn(1, 3000, 80)
+    assert torch.equal(mq.embed_audio(mel), md.embed_audio(mel))
+
+
+def _dequant_like(words, scales, biases):
+    from whisper_mlx_b200.load_models import dequantize
+
+    return dequantize(words, scales, biases, 64, 4)

@@ -198,3 +198,61 @@ def test_load_model_errors(tmp_path):
 
     with pytest.raises(FileNotFoundError):
         load_model(str(tmp_path / "nope"))
+
+
+def test_daemon_tool_module(tmp_path):
+    """The `transcribe_audio` tool follows the reference's plugin protocol (daemon/tools/base.py:23-105): a TOOL with
+    spec + execute, JSON-string results, errors reported as {"error", "status": "error"} instead of raised."""
+    import json
+
+    from whisper_mlx_b200.tool import TOOL
+
+    assert TOOL.name == "transcribe_audio" and TOOL.spec.name == TOOL.name
+    schema = TOOL.to_schema()
+    assert set(schema) == {"name", "description", "parameters"}
+    assert schema["parameters"]["type"] == "object" and schema["parameters"]["required"] == ["file_path"]
+    assert {"file_path", "language", "task", "model"} <= set(schema["parameters"]["properties"])
+    r = json.loads(TOOL.execute(file_path=str(tmp_path / "missing.wav")))
+    assert r["status"] == "error" and "File not found" in r["error"]
+    p = tmp_path / "a.wav"
+    p.write_bytes(b"")
+    r = json.loads(TOOL.execute(file_path=str(p), task="summarise"))
+    assert r["status"] == "error" and "Unsupported task" in r["error"]
+    # a model that cannot be loaded is reported, not raised
+    r = json.loads(TOOL.execute(file_path=str(p), model=str(tmp_path / "no_such_model")))
+    assert r["status"] == "error"
+
+
+def _mlx_quantize(w, group_size, bits):
+    """Reference-side statement of mx.quantize: per group of `group_size` inputs, scale = (max - min) / (2^bits - 1),
+    bias = min, q = round((w - bias) / scale), packed little-endian into uint32 words."""
+    import torch
+
+    o, i = w.shape
+    g = w.view(o, i // group_size, group_size)
+    lo, hi = g.min(-1).values, g.max(-1).values
+    scale = ((hi - lo) / (2 ** bits - 1)).clamp_min(1e-8)
+    q = torch.round((g - lo[..., None]) / scale[..., None]).clamp(0, 2 ** bits - 1).to(torch.int64).view(o, i)
+    per = 32 // bits
+    words = (q.view(o, i // per, per) << (torch.arange(per) * bits)).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    return words.view(torch.uint32) if hasattr(torch, "uint32") else words, scale, lo, (q.view(o, -1, group_size).float() * scale[..., None] + lo[..., None]).view(o, i)
+
+
+@pytest.mark.parametrize("bits,group_size", [(4, 64), (8, 64), (2, 32), (4, 128)])
+def test_mlx_dequantize(bits, group_size):
+    import torch
+
+    from whisper_mlx_b200.load_models import dequantize, dequantize_weights
+
+    torch.manual_seed(bits * 100 + group_size)
+    w = torch.randn(24, 256)
+    words, scales, biases, expect = _mlx_quantize(w, group_size, bits)
+    got = dequantize(words, scales, biases, group_size, bits)
+    assert torch.equal(got, expect)
+    assert (got - w).abs().max().item() <= (w.max() - w.min()).item() / (2 ** bits - 1)
+    # fp16 scales / biases (what the checkpoints store) and the whole-dict form
+    d = dequantize_weights({"a.weight": words, "a.scales": scales.half(), "a.biases": biases.half(), "b.weight": w}, group_size, bits)
+    assert set(d) == {"a.weight", "b.weight"} and d["a.weight"].shape == w.shape
+    with pytest.raises(NotImplementedError):
+        dequantize(words, scales, biases, group_size, 3)

@@ -150,22 +150,40 @@ def _get_tables(device: torch.device, n_mels: int) -> _Tables:
     return _tables[key]
 
 
+def load_audio_pcm16(file: str, sr: int = SAMPLE_RATE) -> np.ndarray:
+    """`load_audio` without its last line: the mono s16le samples as int16.  The log-mel kernel applies the
+    `/ 32768.0` itself (b200w_logmel_pcm16), so a file goes to the GPU at two bytes per sample."""
+    cmd = ["ffmpeg", "-nostdin", "-threads", "0", "-i", file, "-f", "s16le", "-ac", "1", "-acodec", "pcm_s16le",
+           "-ar", str(sr), "-"]
+    try:
+        return np.frombuffer(subprocess.run(cmd, capture_output=True, check=True).stdout, np.int16).flatten()
+    except FileNotFoundError:
+        pcm = _read_wav(file, sr)
+        if pcm is None:
+            raise RuntimeError(f"Failed to load audio: ffmpeg is not installed and {file!r} is not a "
+                               f"{sr} Hz 16-bit PCM WAV file") from None
+        return pcm.flatten()
+    except subprocess.CalledProcessError as e:
+        raise RuntimeError(f"Failed to load audio: {e.stderr.decode()}") from e
+
+
 def _to_device_audio(audio, device=None) -> torch.Tensor:
+    """Samples on the GPU: f32 in [-1, 1], or int16 PCM (files, int16 arrays) which K1 scales itself."""
     if isinstance(audio, str):
-        audio = load_audio(audio)
+        audio = load_audio_pcm16(audio)
     if isinstance(audio, np.ndarray):
-        audio = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
+        audio = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.int16 if audio.dtype == np.int16 else np.float32))
     if not isinstance(audio, torch.Tensor):
         raise TypeError(f"Unsupported audio type: {type(audio)}")
     if not audio.is_cuda:
         if not torch.cuda.is_available():
             raise RuntimeError("log_mel_spectrogram needs a CUDA device (B200); there is no CPU fallback")
         audio = audio.to(device or "cuda", non_blocking=True)
-    return audio.to(torch.float32).contiguous()
+    return audio.to(torch.int16 if audio.dtype == torch.int16 else torch.float32).contiguous()
 
 
 def log_mel_unclamped(audio: torch.Tensor, n_mels: int = 80, padding: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Run K1 on `audio` ((n,) or (n_audio, n) f32 CUDA).  Returns (log10 mel before the clamp, per-audio max).
+    """Run K1 on `audio` ((n,) or (n_audio, n) f32 or int16-PCM CUDA).  Returns (log10 mel before the clamp, per-audio max).
 
     The clamp / scale is applied by `log_mel_spectrogram` (K1b in place) or fused into the bf16 window
     gather that feeds the encoder (`Whisper.mel_windows`).
@@ -180,8 +198,9 @@ def log_mel_unclamped(audio: torch.Tensor, n_mels: int = 80, padding: int = 0) -
     out = torch.empty((n_audio, n_frames, n_mels), dtype=torch.float32, device=x.device)
     gmax = torch.empty((n_audio,), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(lib.b200w_logmel(_lib.ptr(x), n_audio, x.stride(0), n_valid, n_total, n_mels, tb.struct,
-                                    _lib.ptr(out), _lib.ptr(gmax), _lib.stream()))
+        fn = lib.b200w_logmel_pcm16 if x.dtype == torch.int16 else lib.b200w_logmel
+        _lib.check(fn(_lib.ptr(x), n_audio, x.stride(0), n_valid, n_total, n_mels, tb.struct, _lib.ptr(out), _lib.ptr(gmax),
+                      _lib.stream()))
     return out, gmax
 
 
@@ -189,7 +208,8 @@ def log_mel_spectrogram(audio: Union[str, np.ndarray, torch.Tensor], n_mels: int
                         device=None) -> torch.Tensor:
     """Log-mel spectrogram, (frames, n_mels) f32 on the GPU, time-major like the reference.
 
-    `audio`: path (decoded with ffmpeg), NumPy array or torch tensor of 16 kHz mono samples in [-1, 1];
+    `audio`: path (decoded with ffmpeg), NumPy array or torch tensor of 16 kHz mono samples in [-1, 1] (int16
+    arrays are taken as s16le PCM and scaled by 1/32768 on the device);
     `padding` zero samples are appended first.  A 2-D input (n_audio, n) gives (n_audio, frames, n_mels)
     with one clamp maximum per row (the batched contract of BASELINE config 2).
     """

@@ -355,6 +355,13 @@ int b200w_logmel(const float* pcm, int n_audio, long long audio_stride, long lon
                        (cudaStream_t)stream);
 }
 
+int b200w_logmel_pcm16(const int16_t* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
+                       int n_mels, const b200w_logmel_tables* t, float* out_unclamped, float* gmax, void* stream) {
+  B200W_CHECK_ARG(pcm && t && out_unclamped && gmax, "logmel_pcm16: null pointer");
+  return launch_logmel_pcm16(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, t->hann, t->tw400, out_unclamped, gmax,
+                             (cudaStream_t)stream);
+}
+
 int b200w_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, void* stream) {
   B200W_CHECK_ARG(x && gmax && n_audio > 0 && per_audio > 0, "logmel_finalize: bad arguments");
   return launch_logmel_finalize(x, gmax, n_audio, per_audio, (cudaStream_t)stream);

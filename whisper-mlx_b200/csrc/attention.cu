@@ -63,7 +63,6 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, int T, int 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (T + kBKV - 1) / kBKV;
-  pdl_launch_dependents();
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -86,6 +85,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, int T, int 
   const uint32_t tmem_s = tmem_base + ((uint32_t)(warp * 32) << 16);
   const uint32_t tmem_o = tmem_s + 128;
   pdl_wait();
+  pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, kTileBytes);
@@ -271,8 +271,8 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
   __shared__ uint4 s_q[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int unit = blockIdx.x;  // ((b * n_head) + h) * n_q + qi
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   const int qi = unit % n_q, h = (unit / n_q) % n_head, b = unit / (n_q * n_head);
   const int sub = lane & 7, kg = lane >> 3;
   const int d = n_head * kHd;
@@ -484,8 +484,8 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   const int d = n_head * kHd;
   const long long ld = 2ll * d;  // K | V interleaved per row
   const int h = blockIdx.x, b = blockIdx.y, qi = blockIdx.z;
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   const __nv_bfloat16* kbase = cross_kv + (long long)slot[b] * seq_stride + h * kHd + sub * 8;
   const __nv_bfloat16* vbase = kbase + d;
 

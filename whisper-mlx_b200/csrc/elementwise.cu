@@ -18,8 +18,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
                  int rows, int d, __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   if (row >= rows) return;
   const int nvec = d >> 7;  // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * d);
@@ -82,8 +82,8 @@ resid_ln_small_kernel(float* __restrict__ x, const float* __restrict__ part, int
   __shared__ float s_red[2][10];
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const long long off = (long long)row * d + tid * 4;
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   float4 v = *reinterpret_cast<const float4*>(x + off);
   if (n_split > 0) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + tid);
@@ -130,8 +130,8 @@ __global__ void embed_kernel(const int* __restrict__ tokens, int tokens_ld, cons
                              int d, int n_ctx, float* __restrict__ x) {
   const int r = blockIdx.x;  // b * n_q + qi
   const int b = r / n_q, qi = r - b * n_q;
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   int p = pos[b] + qi;
   const int tok = tokens[(long long)b * tokens_ld + p];
   p = min(p, n_ctx - 1);
@@ -197,8 +197,8 @@ filter_argmax_kernel(const float* __restrict__ logits, const uint32_t* __restric
   __shared__ int s_last_ts_idx;
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   const int n = n_tokens[b];
   int* tok = tokens + (long long)b * fp.tokens_ld;
   const float* lg = logits + (long long)b * fp.logits_ld;
@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(1024)
 no_speech_kernel(const float* __restrict__ logits, int logits_ld, int n_vocab, int no_speech, float* __restrict__ out) {
   __shared__ float s_red[32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   const float* lg = logits + (long long)b * logits_ld;
   float mx = -INFINITY;
   for (int v = tid; v < n_vocab; v += 1024) mx = fmaxf(mx, lg[v]);

@@ -54,7 +54,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  pdl_launch_dependents();
 
   const int tiles_m = p.n_batch * p.tiles_m_per_batch;
   const int num_tiles = tiles_m * p.tiles_n * p.split_k;
@@ -82,6 +81,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail; operands and outputs are touched below
+  pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
 
   // tile id -> (m tile, n tile): groups of group_m row tiles sweep all n tiles so the A rows of a group
   // stay L2-resident while W (small) is re-read from L2.

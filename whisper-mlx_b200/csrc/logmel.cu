@@ -64,9 +64,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   buffers 0/1 : sample tile with halo (phases 0-1) -> power spectra [32][203] of the same tile (phases 3-5);
 //                 the other buffer receives the next tile's samples meanwhile
 //   work        : FFT work [16 pairs][409] complex   -> staged log-mel rows [32][129] (phase 5)
-template <int NM>
+// PcmT = float (samples in [-1, 1]) or int16_t (s16le PCM as ffmpeg / a WAV file delivers it: the /32768 scaling of
+// load_audio is applied while the tile is staged, so the int16 -> f32 pass over the file and half of the
+// host-to-device bytes disappear; the shared-memory tile and everything after it are identical).
+template <int NM, typename PcmT>
 __global__ void __launch_bounds__(kLmThreads, 2)
-logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n_valid, long long n_total,
+logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_valid, long long n_total,
               int n_frames, int tiles_per_audio, int n_tiles, LogmelTables tb, float* __restrict__ out,
               float* __restrict__ gmax) {
   constexpr int n_mels = NM;
@@ -78,19 +81,37 @@ logmel_kernel(const float* __restrict__ pcm, long long audio_stride, long long n
   __shared__ float s_red[kLmThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool can_vec = ((audio_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
+  constexpr bool kPcm16 = sizeof(PcmT) == 2;
+  const bool can_vec = ((audio_stride & (kPcm16 ? 7 : 3)) == 0) && ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0);
 
   // phase 0 of a tile: interior tiles stream in asynchronously, edge tiles (reflect / zero extension) synchronously
   auto stage_tile = [&](float* dst, int t) {
     const int a = t / tiles_per_audio;
     const long long base = (long long)(t - a * tiles_per_audio) * kFrames * kHop - kNfft / 2;
-    const float* x = pcm + (long long)a * audio_stride;
+    const PcmT* x = pcm + (long long)a * audio_stride;
     if (can_vec && base >= 0 && base + kTile <= n_valid) {
-      for (int i = tid; i < kTile / 4; i += kLmThreads) cp_async16(dst + 4 * i, x + base + 4 * i);  // base % 8 == 0
+      if constexpr (kPcm16) {
+        static_assert(kTile % 8 == 0, "eight samples per 16-byte load");
+        for (int i = tid; i < kTile / 8; i += kLmThreads) {  // base % 8 == 0
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + base) + i);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            f[2 * k] = (float)(short)(w[k] & 0xffffu) * (1.0f / 32768.0f);
+            f[2 * k + 1] = (float)(short)(w[k] >> 16) * (1.0f / 32768.0f);
+          }
+          *reinterpret_cast<float4*>(dst + 8 * i) = make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(dst + 8 * i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
+      } else {
+        for (int i = tid; i < kTile / 4; i += kLmThreads) cp_async16(dst + 4 * i, x + base + 4 * i);  // base % 8 == 0
+      }
     } else {
       for (int i = tid; i < kTile; i += kLmThreads) {
         const long long j = lm::reflect_index(base + i, n_valid, n_total);
-        dst[i] = (j >= 0) ? __ldg(x + j) : 0.0f;
+        if constexpr (kPcm16) dst[i] = (j >= 0) ? (float)__ldg(x + j) * (1.0f / 32768.0f) : 0.0f;
+        else dst[i] = (j >= 0) ? __ldg(x + j) : 0.0f;
       }
     }
     cp_async_commit();
@@ -273,15 +294,18 @@ static size_t logmel_smem_bytes() {
 int init_logmel() {
   static bool done = false;
   if (done) return kOk;
-  B200W_CUDA_OK(cudaFuncSetAttribute(logmel_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_smem_bytes()));
-  B200W_CUDA_OK(cudaFuncSetAttribute(logmel_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_smem_bytes()));
+  B200W_CUDA_OK(cudaFuncSetAttribute(logmel_kernel<80, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_smem_bytes()));
+  B200W_CUDA_OK(cudaFuncSetAttribute(logmel_kernel<128, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_smem_bytes()));
+  B200W_CUDA_OK(cudaFuncSetAttribute(logmel_kernel<80, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_smem_bytes()));
+  B200W_CUDA_OK(cudaFuncSetAttribute(logmel_kernel<128, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)logmel_smem_bytes()));
   done = true;
   return kOk;
 }
 
-int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
-                  int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
-                  cudaStream_t stream) {
+template <typename PcmT>
+static int launch_logmel_t(const PcmT* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
+                           int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
+                           cudaStream_t stream) {
   B200W_CHECK_ARG(n_audio > 0 && n_valid > kNfft / 2 && n_total >= n_valid, "logmel: bad sizes");
   B200W_CHECK_ARG(n_mels == 80 || n_mels == 128, "logmel: n_mels must be 80 or 128, got %d", n_mels);
   const long long n_frames_ll = n_total / kHop;
@@ -299,14 +323,26 @@ int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long lo
   const int n_tiles = (int)n_tiles_ll;
   const int grid = n_tiles < 2 * device_sm_count() ? n_tiles : 2 * device_sm_count();
   if (n_mels == 80)
-    logmel_kernel<80><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, tiles_per_audio,
-                                                          n_tiles, tb, out_unclamped, gmax);
+    logmel_kernel<80, PcmT><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames,
+                                                                tiles_per_audio, n_tiles, tb, out_unclamped, gmax);
   else
-    logmel_kernel<128><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, tiles_per_audio,
-                                                           n_tiles, tb, out_unclamped, gmax);
+    logmel_kernel<128, PcmT><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames,
+                                                                 tiles_per_audio, n_tiles, tb, out_unclamped, gmax);
   B200W_LAUNCH_OK();
   count_launch(2);
   return kOk;
+}
+
+int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
+                  int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
+                  cudaStream_t stream) {
+  return launch_logmel_t(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, hann, tw400, out_unclamped, gmax, stream);
+}
+
+int launch_logmel_pcm16(const int16_t* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
+                        int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
+                        cudaStream_t stream) {
+  return launch_logmel_t(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, hann, tw400, out_unclamped, gmax, stream);
 }
 
 int launch_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, cudaStream_t stream) {

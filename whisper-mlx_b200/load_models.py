@@ -3,7 +3,8 @@
 
 Reads the on-disk format the reference consumes -- `config.json` (the ten ModelDimensions fields,
 optionally `model_type` / `quantization`) and `weights.safetensors` or `weights.npz` with MLX parameter
-names and layouts -- into bf16 / f32 torch CUDA tensors.
+names and layouts -- into bf16 / f32 torch CUDA tensors.  MLX group-quantised
+checkpoints (2/4/8 bit) are expanded to dense weights at load; the kernels compute in bf16.
 """
 from __future__ import annotations
 
@@ -30,6 +31,32 @@ def _read_weights(model_path: Path) -> Dict[str, torch.Tensor]:
     raise FileNotFoundError(f"no weights.safetensors or weights.npz under {model_path}")
 
 
+def dequantize(wq: torch.Tensor, scales: torch.Tensor, biases: torch.Tensor, group_size: int, bits: int) -> torch.Tensor:
+    """MLX affine group quantisation -> f32.  `wq` is (out, in * bits / 32) uint32 with element j of a word at bits
+    [j * bits, (j + 1) * bits); every `group_size` consecutive input elements share `scales[o, g]` / `biases[o, g]`:
+    w = scale * q + bias (mx.quantize / nn.QuantizedLinear, UPSTREAM)."""
+    if bits not in (2, 4, 8):
+        raise NotImplementedError(f"MLX quantisation with bits={bits} is not supported (2, 4 or 8)")
+    words = wq.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    shifts = torch.arange(0, 32, bits, dtype=torch.int64)
+    q = ((words[..., None] >> shifts) & ((1 << bits) - 1)).reshape(words.shape[0], -1).to(torch.float32)
+    out_dim, in_dim = q.shape
+    if in_dim != scales.shape[-1] * group_size or scales.shape != biases.shape:
+        raise ValueError(f"quantised weight {tuple(wq.shape)} does not match scales {tuple(scales.shape)} at group_size={group_size}")
+    q = q.view(out_dim, -1, group_size)
+    return (q * scales.to(torch.float32)[..., None] + biases.to(torch.float32)[..., None]).view(out_dim, in_dim)
+
+
+def dequantize_weights(weights: Dict[str, torch.Tensor], group_size: int = 64, bits: int = 4) -> Dict[str, torch.Tensor]:
+    """Replace every (`X.weight` uint32, `X.scales`, `X.biases`) triple by a dense `X.weight`; the engine stores bf16."""
+    out = dict(weights)
+    for key in [k for k in weights if k.endswith(".scales")]:
+        base = key[: -len(".scales")]
+        out[base + ".weight"] = dequantize(weights[base + ".weight"], weights[key], weights[base + ".biases"], group_size, bits)
+        del out[key], out[base + ".biases"]
+    return out
+
+
 def load_model(path_or_hf_repo: str, dtype: torch.dtype = torch.bfloat16, device=None) -> Whisper:
     """Load a Whisper model from a local directory or a Hugging Face repo id (MLX-format weights)."""
     model_path = Path(path_or_hf_repo)
@@ -46,10 +73,10 @@ def load_model(path_or_hf_repo: str, dtype: torch.dtype = torch.bfloat16, device
         config = json.loads(f.read())
         config.pop("model_type", None)
         quantization = config.pop("quantization", None)
-    if quantization is not None:
-        raise NotImplementedError("MLX-quantised checkpoints are not supported yet; use the 16-bit weights")
     model_args = ModelDimensions(**config)
     weights = _read_weights(model_path)
+    if quantization is not None:  # MLX-quantised checkpoint (e.g. the 4-bit mlx-community variants): expand at load
+        weights = dequantize_weights(weights, int(quantization.get("group_size", 64)), int(quantization.get("bits", 4)))
     weights.pop("alignment_heads", None)
     weights = {k: v for k, v in weights.items() if not k.endswith("encoder.positional_embedding")}
     model = Whisper(model_args, weights, device=device, dtype=dtype)
