@@ -178,3 +178,34 @@ def _dequant_like(words, scales, biases):
     from whisper_mlx_b200.load_models import dequantize
 
     return dequantize(words, scales, biases, 64, 4)
+
+
+def test_finished_sequences_are_skipped_without_touching_the_others(micro_dir):
+    """Sequences that have emitted EOT stop streaming their K/V in the attention kernels (decoder_step passes the
+    `finished` flags while sampling): their tokens stay EOT and every other sequence decodes exactly as before."""
+    from whisper_mlx_b200.decoding import DecodeSession, DecodingOptions, DecodingTask
+    from whisper_mlx_b200.load_models import load_model
+
+    m = load_model(micro_dir)
+    g = torch.Generator().manual_seed(3)
+    xa = torch.randn(4, 1500, 128, generator=g).bfloat16().cuda()
+    task = DecodingTask(m, DecodingOptions(language="en", sample_len=12))
+    eot, n0 = task.tokenizer.eot, len(task.initial_tokens)
+
+    def run(stop):
+        sess = DecodeSession(m, xa, 1, max_tokens=n0 + 12)
+        sess.set_tokens(torch.tensor(task.initial_tokens, dtype=torch.int32).repeat(4, 1))
+        sess.set_filter(task._filter_params(sess), task._get_suppress_tokens())
+        sess.prompt_step(n0, task.sot_index)
+        for b in stop:  # pretend the first sampled token of these sequences was EOT
+            sess.tokens[b, n0] = eot
+            sess.finished[b] = 1
+        for _ in range(10):
+            sess.sample_step()
+        torch.cuda.synchronize()
+        return sess.tokens[:, : n0 + 11].cpu()
+
+    full, part = run([]), run([1, 3])
+    assert torch.equal(full[0], part[0]) and torch.equal(full[2], part[2])
+    assert bool((part[1, n0:] == eot).all()) and bool((part[3, n0:] == eot).all())
+    assert not bool((full[1, n0:] == eot).all())

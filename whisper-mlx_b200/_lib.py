@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200whisper.so")
+LIB_PATH = os.environ.get("B200W_LIB") or os.path.join(_HERE, "csrc", "libb200whisper.so")  # B200W_LIB: A/B builds
 
 _lock = threading.Lock()
 _lib = None

@@ -616,6 +616,8 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   B200W_TRY(launch_embed(st->tokens, st->tokens_ld, st->pos, B, n_q, (const __nv_bfloat16*)m.w.tok_emb,
                          (const __nv_bfloat16*)m.w.dec_pos, d, dm.n_text_ctx, x, stream));
   const bool small = rows <= 128 && n_q == 1;  // decode steps: split-K GEMMs whose reduction is fused into the consumers
+  // while sampling, sequences that have emitted EOT stop streaming their K/V (their tokens are forced to EOT by K9)
+  const int* done = select ? st->finished : nullptr;
   if (small) {
     const int bn = 64;
     const long long s3 = 128ll * 3 * d, s1 = 128ll * d;
@@ -632,13 +634,13 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
       B200W_TRY(gemm_splitk(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.part_qkv, 3 * d, s3, sp_qkv, bn, stream, "dec_gemm_qkv"));
       B200W_TRY(launch_decoder_self_attention(nullptr, B, 1, H, st->pos, kp, vp, st->block_table, st->max_pages,
                                               st->page_size, (__nv_bfloat16*)bf.att, stream, bf.part_qkv, sp_qkv, s3,
-                                              L.b_qkv));
+                                              L.b_qkv, done));
       B200W_TRY(gemm_splitk(bf.att, d, rows, L.w_out, d, d, bf.part_res, d, s1, sp_d, bn, stream, "dec_gemm_out"));
       B200W_TRY(launch_resid_ln_small(x, bf.part_res, sp_d, s1, L.b_out, L.cross_ln_g, L.cross_ln_b, rows, d,
                                       (__nv_bfloat16*)bf.h, stream));
       B200W_TRY(gemm_splitk(bf.h, d, rows, L.w_cq, d, d, bf.part_q, d, s1, sp_d, bn, stream, "dec_gemm_cq"));
       B200W_TRY(launch_decoder_cross_attention(nullptr, B, 1, H, ckv, (long long)T * 2 * d, T, st->cross_slot,
-                                               (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq));
+                                               (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq, done));
       B200W_TRY(gemm_splitk(bf.att, d, rows, L.w_cout, d, d, bf.part_res, d, s1, sp_d, bn, stream, "dec_gemm_cout"));
       B200W_TRY(launch_resid_ln_small(x, bf.part_res, sp_d, s1, L.b_cout, L.mlp_ln_g, L.mlp_ln_b, rows, d,
                                       (__nv_bfloat16*)bf.h, stream));
@@ -658,12 +660,13 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
       B200W_TRY(launch_layernorm(x, L.attn_ln_g, L.attn_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
       B200W_TRY(gemm(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.qkv, 3 * d, false, L.b_qkv, false, nullptr, 0, 0, stream));
       B200W_TRY(launch_decoder_self_attention((const __nv_bfloat16*)bf.qkv, B, n_q, H, st->pos, kp, vp, st->block_table,
-                                              st->max_pages, st->page_size, (__nv_bfloat16*)bf.att, stream));
+                                              st->max_pages, st->page_size, (__nv_bfloat16*)bf.att, stream, nullptr, 0, 0,
+                                              nullptr, done));
       B200W_TRY(gemm(bf.att, d, rows, L.w_out, d, d, x, d, true, L.b_out, false, x, d, 0, stream));
       B200W_TRY(launch_layernorm(x, L.cross_ln_g, L.cross_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
       B200W_TRY(gemm(bf.h, d, rows, L.w_cq, d, d, bf.qc, d, false, L.b_cq, false, nullptr, 0, 0, stream));
       B200W_TRY(launch_decoder_cross_attention((const __nv_bfloat16*)bf.qc, B, n_q, H, ckv, (long long)T * 2 * d, T,
-                                               st->cross_slot, (__nv_bfloat16*)bf.att, stream));
+                                               st->cross_slot, (__nv_bfloat16*)bf.att, stream, nullptr, 0, 0, nullptr, done));
       B200W_TRY(gemm(bf.att, d, rows, L.w_cout, d, d, x, d, true, L.b_cout, false, x, d, 0, stream));
       B200W_TRY(launch_layernorm(x, L.mlp_ln_g, L.mlp_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
       B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));

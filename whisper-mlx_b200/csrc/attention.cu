@@ -264,7 +264,7 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
                               const int* __restrict__ pos, __nv_bfloat16* k_pages, __nv_bfloat16* v_pages,
                               const int* __restrict__ block_table, int max_pages, int page_size,
                               __nv_bfloat16* __restrict__ out, const float* __restrict__ part, int n_split,
-                              long long split_stride, const float* __restrict__ bias) {
+                              long long split_stride, const float* __restrict__ bias, const int* __restrict__ finished) {
   __shared__ float s_p[kMaxSelfKeys];
   __shared__ float s_red[kSelfWarps];
   __shared__ float s_part[kSelfWarps][kHd];
@@ -274,6 +274,7 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
   pdl_wait();
   pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   const int qi = unit % n_q, h = (unit / n_q) % n_head, b = unit / (n_q * n_head);
+  if (finished != nullptr && finished[b]) return;  // the sequence has emitted EOT: its row is ignored from here on
   const int sub = lane & 7, kg = lane >> 3;
   const int d = n_head * kHd;
   const int p0 = pos[b];           // tokens already cached for this sequence
@@ -448,7 +449,8 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
 int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, int n_head, const int* pos,
                                   __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, const int* block_table,
                                   int max_pages_per_seq, int page_size, __nv_bfloat16* out, cudaStream_t stream,
-                                  const float* part, int n_split, long long split_stride, const float* bias) {
+                                  const float* part, int n_split, long long split_stride, const float* bias,
+                                  const int* finished) {
   B200W_CHECK_ARG(n_split == 0 || (n_q == 1 && part && bias), "self_attention: split-K input needs n_q == 1");
   B200W_CHECK_ARG(n_split > 0 || qkv, "self_attention: null qkv");
   B200W_CHECK_ARG(n_seq > 0 && n_q > 0 && (long long)n_seq * n_q * n_head < (1ll << 30), "self_attention: bad sizes");
@@ -458,7 +460,7 @@ int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, 
   ProfScope prof_("decoder_self_attention", stream);
   B200W_CUDA_OK(launch_k(decoder_self_attention_kernel, dim3(units), dim3(kSelfThreads), 0, stream,
                          qkv, n_seq, n_q, n_head, pos, k_pages, v_pages, block_table, max_pages_per_seq, page_size, out,
-                         part, n_split, split_stride, bias));
+                         part, n_split, split_stride, bias, finished));
   count_launch();
   return kOk;
 }
@@ -467,13 +469,20 @@ int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, 
 constexpr int kCrossThreads = 256;
 constexpr int kCrossWarps = kCrossThreads / 32;
 constexpr int kMaxCrossKeys = 1536;
+#ifndef B200W_CROSS_UNROLL
+#define B200W_CROSS_UNROLL 8
+#endif
+// 16-byte loads in flight per thread.  The kernel is bound by bytes in flight, not by DRAM: measured on B200 at the
+// bench shape (CUDA events, incl. ~5 us event overhead) 4 -> 186 us, 6 -> 184, 8 -> 159, 12 -> 177, 16 -> 204
+// (registers 48 / 56 / 64 / 96 / 128 cut the resident CTAs); prefetching V across the softmax barriers: 176.
+constexpr int kCrossUnroll = B200W_CROSS_UNROLL;
 
 __global__ void __launch_bounds__(kCrossThreads)
 decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int n_head,
                                const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride, int T,
                                const int* __restrict__ slot, __nv_bfloat16* __restrict__ out,
                                const float* __restrict__ part, int n_split, long long split_stride,
-                               const float* __restrict__ bias) {
+                               const float* __restrict__ bias, const int* __restrict__ finished) {
   __shared__ float s_p[kMaxCrossKeys];
   __shared__ float s_red[kCrossWarps];
   __shared__ float s_part[kCrossWarps][kHd];
@@ -486,6 +495,7 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   const int h = blockIdx.x, b = blockIdx.y, qi = blockIdx.z;
   pdl_wait();
   pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
+  if (finished != nullptr && finished[b]) return;  // no K/V streaming for sequences that have emitted EOT
   const __nv_bfloat16* kbase = cross_kv + (long long)slot[b] * seq_stride + h * kHd + sub * 8;
   const __nv_bfloat16* vbase = kbase + d;
 
@@ -512,18 +522,18 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
     qv[4] = a2.x * c; qv[5] = a2.y * c; qv[6] = a3.x * c; qv[7] = a3.y * c;
   }
 
-  // ---- scores: 4 keys per warp per load instruction, 4 loads in flight per thread ----
+  // ---- scores: 4 keys per warp per load instruction, kCrossUnroll loads in flight per thread ----
   constexpr int kStep = kCrossWarps * 4;  // keys per CTA sweep
   float mx = -INFINITY;
-  for (int j0 = warp * 4; j0 < T; j0 += 4 * kStep) {  // warp-uniform trip count: the shuffles need every lane
-    uint4 u[4];
+  for (int j0 = warp * 4; j0 < T; j0 += kCrossUnroll * kStep) {  // warp-uniform trip count: the shuffles need every lane
+    uint4 u[kCrossUnroll];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kCrossUnroll; ++i) {
       const int j = j0 + kg + i * kStep;
       u[i] = (j < T) ? __ldg(reinterpret_cast<const uint4*>(kbase + j * ld)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kCrossUnroll; ++i) {
       const int j = j0 + kg + i * kStep;
       const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z),
                    a3 = unpack_bf16x2(u[i].w);
@@ -568,17 +578,17 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-  for (int j0 = warp * 4; j0 < T; j0 += 4 * kStep) {
-    uint4 u[4];
-    float p[4];
+  for (int j0 = warp * 4; j0 < T; j0 += kCrossUnroll * kStep) {
+    uint4 u[kCrossUnroll];
+    float p[kCrossUnroll];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kCrossUnroll; ++i) {
       const int j = j0 + kg + i * kStep;
       u[i] = (j < T) ? __ldg(reinterpret_cast<const uint4*>(vbase + j * ld)) : make_uint4(0, 0, 0, 0);
       p[i] = (j < T) ? s_p[j] : 0.0f;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kCrossUnroll; ++i) {
       const float2 a0 = unpack_bf16x2(u[i].x), a1 = unpack_bf16x2(u[i].y), a2 = unpack_bf16x2(u[i].z),
                    a3 = unpack_bf16x2(u[i].w);
       acc[0] = fmaf(p[i], a0.x, acc[0]);
@@ -612,14 +622,14 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
 int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, int n_head,
                                    const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
                                    __nv_bfloat16* out, cudaStream_t stream, const float* part, int n_split,
-                                   long long split_stride, const float* bias) {
+                                   long long split_stride, const float* bias, const int* finished) {
   B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "cross_attention: bad sizes");
   B200W_CHECK_ARG(n_split > 0 ? (part && bias) : (q != nullptr), "cross_attention: missing query input");
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
   dim3 grid(n_head, n_seq, n_q);
   ProfScope prof_("decoder_cross_attention", stream);
   B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head, cross_kv,
-                         seq_stride, T, slot, out, part, n_split, split_stride, bias));
+                         seq_stride, T, slot, out, part, n_split, split_stride, bias, finished));
   count_launch();
   return kOk;
 }

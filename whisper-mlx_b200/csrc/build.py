@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
     "-I" + os.path.join(REPO, "include"), "-I" + HERE,
     "-cudart", "static",
-]
+] + os.environ.get("B200W_NVCC_EXTRA", "").split()  # e.g. -DB200W_CROSS_UNROLL=4 for A/B builds (tools/time_cross.py)
 
 
 def _digest() -> str:

@@ -88,9 +88,14 @@ resid_ln_small_kernel(float* __restrict__ x, const float* __restrict__ part, int
   if (n_split > 0) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + tid);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-    for (int s = 0; s < n_split; ++s) {
-      const float4 p = *reinterpret_cast<const float4*>(part + s * split_stride + off);
-      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    // all slabs in flight at once (n_split <= 8): one L2 round trip instead of one per slab
+    float4 p[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      p[s] = (s < n_split) ? *reinterpret_cast<const float4*>(part + s * split_stride + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      v.x += p[s].x; v.y += p[s].y; v.z += p[s].z; v.w += p[s].w;
     }
     *reinterpret_cast<float4*>(x + off) = v;
   }
@@ -117,6 +122,7 @@ int launch_resid_ln_small(float* x, const float* part, int n_split, long long sp
                           cudaStream_t stream) {
   B200W_CHECK_ARG(rows > 0 && d % 128 == 0 && d <= 1280, "resid_ln: unsupported d=%d", d);
   B200W_CHECK_ARG(n_split == 0 || (part != nullptr && bias != nullptr), "resid_ln: partials without bias");
+  B200W_CHECK_ARG(n_split >= 0 && n_split <= 8, "resid_ln: at most 8 partial slabs (got %d)", n_split);
   ProfScope prof_("resid_ln", stream);
   B200W_CUDA_OK(launch_k(resid_ln_small_kernel, dim3(rows), dim3(d / 4), 0, stream, x, part, n_split, split_stride, bias,
                          gamma, beta, d, out_bf16));

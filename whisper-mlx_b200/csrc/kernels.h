@@ -86,10 +86,11 @@ int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, 
                                   __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, const int* block_table,
                                   int max_pages_per_seq, int page_size, __nv_bfloat16* out, cudaStream_t stream,
                                   const float* part = nullptr, int n_split = 0, long long split_stride = 0,
-                                  const float* bias = nullptr);
+                                  const float* bias = nullptr, const int* finished = nullptr);
 int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, int n_head,
                                    const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
                                    __nv_bfloat16* out, cudaStream_t stream, const float* part = nullptr,
-                                   int n_split = 0, long long split_stride = 0, const float* bias = nullptr);
+                                   int n_split = 0, long long split_stride = 0, const float* bias = nullptr,
+                                   const int* finished = nullptr);
 
 }  // namespace b200w
