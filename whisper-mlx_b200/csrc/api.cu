@@ -68,6 +68,16 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+// B200W_CHAIN=0 runs every small-M phase of a decode step as its own launch (the pre-chain path, kept for A/B)
+static bool chain_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200W_CHAIN");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 bool gemm2_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -268,7 +278,9 @@ static size_t carve_encoder(const b200w_dims& dm, int B, Carver& c, EncBufs* o) 
 struct DecBufs {
   void *x, *h, *qkv, *att, *qc, *mlp;
   float *part_qkv, *part_q, *part_res;  // split-K partial slabs (decode steps with <= 128 rows)
+  unsigned int* counters;               // grid-barrier counters of the chain launches of one step
 };
+constexpr int kChainCounters = 256;
 constexpr int kMaxSplit = 8;
 static size_t carve_decoder(const b200w_dims& dm, int n_seq, int n_q, Carver& c, DecBufs* o) {
   const size_t d = dm.n_text_state;
@@ -285,7 +297,8 @@ static size_t carve_decoder(const b200w_dims& dm, int n_seq, int n_q, Carver& c,
     p1 = static_cast<float*>(c.take((size_t)kMaxSplit * 128 * d * 4));
     pr = static_cast<float*>(c.take((size_t)kMaxSplit * 128 * d * 4));
   }
-  if (o) *o = DecBufs{x, h, qkv, att, qc, mlp, pq, p1, pr};
+  unsigned int* counters = static_cast<unsigned int*>(c.take(kChainCounters * sizeof(unsigned int)));
+  if (o) *o = DecBufs{x, h, qkv, att, qc, mlp, pq, p1, pr, counters};
   return c.off;
 }
 
@@ -618,7 +631,63 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   const bool small = rows <= 128 && n_q == 1;  // decode steps: split-K GEMMs whose reduction is fused into the consumers
   // while sampling, sequences that have emitted EOT stop streaming their K/V (their tokens are forced to EOT by K9)
   const int* done = select ? st->finished : nullptr;
-  if (small) {
+  if (small && chain_enabled() && rows <= device_sm_count() && 2 * dm.n_text_layer + 2 <= kChainCounters) {
+    // K11: the small-M phases between the attention kernels run as three chains per layer
+    //   [LN -> QKV]  SA  [out -> LN -> q]  CA  [out -> LN -> MLP1 -> MLP2 -> LN -> next layer's QKV]
+    const long long s3 = 128ll * 3 * d, s1 = 128ll * d;
+    const int sp_qkv = plan_split_k(3 * d, d, 64), sp_d = plan_split_k(d, d, 64), sp_mlp2 = plan_split_k(d, 4 * d, 64);
+    B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, kChainCounters * sizeof(unsigned int), stream));
+    int n_chain = 0;
+    __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(bf.h);
+    {
+      const b200w_dec_layer& L = m.dec[0];
+      ChainMaps maps;
+      ChainParams cp{};
+      cp.rows = rows;
+      cp.counter = bf.counters + n_chain++;
+      B200W_TRY(chain_add_ln(&cp, x, nullptr, 0, 0, nullptr, L.attn_ln_g, L.attn_ln_b, d, hb));
+      B200W_TRY(chain_add_gemm(&maps, &cp, bf.h, d, L.w_qkv, 3 * d, d, sp_qkv, bf.part_qkv, 3 * d, s3, nullptr, false));
+      B200W_TRY(launch_chain(maps, cp, stream));
+    }
+    for (int l = 0; l < dm.n_text_layer; ++l) {
+      const b200w_dec_layer& L = m.dec[l];
+      __nv_bfloat16* kp = static_cast<__nv_bfloat16*>(st->k_pages) + (size_t)l * st->layer_page_stride;
+      __nv_bfloat16* vp = static_cast<__nv_bfloat16*>(st->v_pages) + (size_t)l * st->layer_page_stride;
+      const __nv_bfloat16* ckv = static_cast<const __nv_bfloat16*>(st->cross_kv) + (size_t)l * st->cross_layer_stride;
+      B200W_TRY(launch_decoder_self_attention(nullptr, B, 1, H, st->pos, kp, vp, st->block_table, st->max_pages,
+                                              st->page_size, (__nv_bfloat16*)bf.att, stream, bf.part_qkv, sp_qkv, s3,
+                                              L.b_qkv, done));
+      {
+        ChainMaps maps;
+        ChainParams cp{};
+        cp.rows = rows;
+        cp.counter = bf.counters + n_chain++;
+        B200W_TRY(chain_add_gemm(&maps, &cp, bf.att, d, L.w_out, d, d, sp_d, bf.part_res, d, s1, nullptr, false));
+        B200W_TRY(chain_add_ln(&cp, x, bf.part_res, sp_d, s1, L.b_out, L.cross_ln_g, L.cross_ln_b, d, hb));
+        B200W_TRY(chain_add_gemm(&maps, &cp, bf.h, d, L.w_cq, d, d, sp_d, bf.part_q, d, s1, nullptr, false));
+        B200W_TRY(launch_chain(maps, cp, stream));
+      }
+      B200W_TRY(launch_decoder_cross_attention(nullptr, B, 1, H, ckv, (long long)T * 2 * d, T, st->cross_slot,
+                                               (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq, done));
+      {
+        const bool last = l + 1 == dm.n_text_layer;
+        ChainMaps maps;
+        ChainParams cp{};
+        cp.rows = rows;
+        cp.counter = bf.counters + n_chain++;
+        B200W_TRY(chain_add_gemm(&maps, &cp, bf.att, d, L.w_cout, d, d, sp_d, bf.part_res, d, s1, nullptr, false));
+        B200W_TRY(chain_add_ln(&cp, x, bf.part_res, sp_d, s1, L.b_cout, L.mlp_ln_g, L.mlp_ln_b, d, hb));
+        B200W_TRY(chain_add_gemm(&maps, &cp, bf.h, d, L.w_mlp1, 4 * d, d, 1, bf.mlp, 4 * d, 0, L.b_mlp1, true));
+        B200W_TRY(chain_add_gemm(&maps, &cp, bf.mlp, 4 * d, L.w_mlp2, d, 4 * d, sp_mlp2, bf.part_res, d, s1, nullptr, false));
+        B200W_TRY(chain_add_ln(&cp, x, bf.part_res, sp_mlp2, s1, L.b_mlp2, last ? m.w.dec_ln_g : m.dec[l + 1].attn_ln_g,
+                               last ? m.w.dec_ln_b : m.dec[l + 1].attn_ln_b, d, hb));
+        if (!last)
+          B200W_TRY(chain_add_gemm(&maps, &cp, bf.h, d, m.dec[l + 1].w_qkv, 3 * d, d, sp_qkv, bf.part_qkv, 3 * d, s3, nullptr,
+                                   false));
+        B200W_TRY(launch_chain(maps, cp, stream));
+      }
+    }
+  } else if (small) {
     const int bn = 64;
     const long long s3 = 128ll * 3 * d, s1 = 128ll * d;
     const int sp_qkv = plan_split_k(3 * d, d, bn), sp_d = plan_split_k(d, d, bn), sp_mlp2 = plan_split_k(d, 4 * d, bn);

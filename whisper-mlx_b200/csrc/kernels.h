@@ -61,6 +61,43 @@ int make_tmap_w(CUtensorMap* out, const void* w, int N, int K, int block_n);
 int make_tmap_a(CUtensorMap* out, const void* a, int n_batch, int rows, int K, long long row_stride,
                 long long batch_stride);
 
+// ---------------------------------------------------------------------------------------- K11 decode chain
+// Up to kChainMaxPhases small-M phases (GEMM with split-K slabs or bias+GELU, residual+LayerNorm) of a decoder layer
+// in one cooperative launch with grid barriers between them (chain.cu).
+constexpr int kChainMaxPhases = 6;
+constexpr int kChainMaxGemm = 4;
+constexpr int kChainGemm = 0, kChainLn = 1;
+struct ChainPhase {
+  int kind;
+  // GEMM: out = A (rows, K) W (N, K)^T; split_k raw fp32 slabs (gelu == 0) or bias + GELU -> bf16 (gelu == 1)
+  int map, tiles_n, split_k, kb_per_split, num_kb, gelu;
+  void* out;
+  long long ldc;
+  // LayerNorm: x += bias + sum of n_split slabs of `part`; h = LN(x) * gamma + beta as bf16
+  int n_split, d;
+  float* x;
+  const float* part;
+  const float *gamma, *beta;
+  __nv_bfloat16* h;
+  // both
+  const float* bias;
+  long long split_stride;
+};
+struct ChainParams {
+  int n_phases, n_gemm, rows;
+  unsigned int* counter;  // zero on entry; one per launch
+  ChainPhase ph[kChainMaxPhases];
+};
+struct ChainMaps {
+  CUtensorMap a[kChainMaxGemm], b[kChainMaxGemm];
+};
+int init_chain();
+int chain_add_gemm(ChainMaps* maps, ChainParams* p, const void* A, long long lda, const void* W, int N, int K, int split_k,
+                   void* out, long long ldc, long long split_stride, const float* bias, bool gelu);
+int chain_add_ln(ChainParams* p, float* x, const float* part, int n_split, long long split_stride, const float* bias,
+                 const float* gamma, const float* beta, int d, __nv_bfloat16* h);
+int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------- K4 / K10 / K9
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
                      float* out_f32, cudaStream_t stream);
