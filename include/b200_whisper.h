@@ -290,6 +290,30 @@ size_t b200w_decoder_workspace_bytes(const b200w_model* m, int n_seq, int n_q);
 int b200w_decoder_step(const b200w_model* m, const b200w_decode_state* st, int n_q, int sot_index, int select,
                        const b200w_filter_params* fp, void* workspace, size_t workspace_bytes, void* stream);
 
+/* -------------------------------------------------------------------------------------------------
+ * Word-level timestamps (UPSTREAM mlx_whisper/timing.py)
+ * ------------------------------------------------------------------------------------------------- */
+/* Teacher-forced forward over the n_q loaded tokens of every sequence (the decoder half of UPSTREAM
+ * whisper.py::Whisper.forward_with_cross_qk): the logits of EVERY position go to logits_all
+ * ((n_seq * n_q, logits_ld) f32, may be NULL) and the cross-attention probabilities of the layers
+ * >= probs_first_layer to cross_probs ((n_text_layer - probs_first_layer, n_seq, n_q, n_text_head, 1500) f32,
+ * may be NULL).  Same workspace as b200w_decoder_step(n_seq, n_q). */
+int b200w_decoder_forward_full(const b200w_model* m, const b200w_decode_state* st, int n_q, void* workspace,
+                               size_t workspace_bytes, float* logits_all, float* cross_probs, int probs_first_layer,
+                               void* stream);
+/* timing.py::find_alignment's matrix for sequence `seq`: the probabilities of the n_sel selected (layer - first
+ * layer, head) pairs `heads` (device, 2 * n_sel ints) are renormalised over the first n_frames frames, normalised
+ * over the token axis ((w - mean) / std), median-filtered (width 7, reflect padding) along frames and averaged over
+ * the heads -> matrix (n_q, n_frames) f32.  stats: workspace of 2 * n_sel * n_frames + n_sel * n_q floats. */
+int b200w_alignment_matrix(const float* cross_probs, int n_layers_stored, int n_seq, int seq, int n_q, int n_head,
+                           int n_ctx, const int* heads, int n_sel, int n_frames, float* stats, float* matrix,
+                           void* stream);
+/* timing.py::dtw on -matrix (N rows of M columns, row stride ld): monotonic alignment path, written BACK TO FRONT to
+ * text_idx / time_idx (N + M ints each) with its length in path_len (device).  cost: (N + 1) * (M + 1) floats and
+ * trace: as many bytes of workspace. */
+int b200w_dtw(const float* matrix, long long ld, int N, int M, float* cost, signed char* trace, int* text_idx,
+              int* time_idx, int* path_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

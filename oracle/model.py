@@ -150,8 +150,10 @@ def encoder_forward(w: dict, dims: ModelDimensions, mel: torch.Tensor, policy="f
 
 @torch.no_grad()
 def decoder_forward(w: dict, dims: ModelDimensions, tokens: torch.Tensor, xa: torch.Tensor,
-                    kv_cache=None, policy="fp32"):
-    """TextDecoder. tokens (B, n) int64, xa (B, 1500, d) -> logits (B, n, V), cache."""
+                    kv_cache=None, policy="fp32", return_cross_qk=False):
+    """TextDecoder. tokens (B, n) int64, xa (B, 1500, d) -> logits (B, n, V), cache.
+    return_cross_qk: also the per-layer cross-attention scores (B, H, n, 1500) before the softmax, as
+    Whisper.forward_with_cross_qk hands them to timing.py."""
     offset = kv_cache[0][0][0].shape[1] if kv_cache else 0
     n = tokens.shape[-1]
     x = w["decoder.token_embedding.weight"][tokens] + w["decoder.positional_embedding"][offset : offset + n]
@@ -159,11 +161,14 @@ def decoder_forward(w: dict, dims: ModelDimensions, tokens: torch.Tensor, xa: to
         kv_cache = [None] * dims.n_text_layer
     mask = torch.full((n, offset + n), float("-inf")).triu_(offset + 1) if n > 1 else None
     xa = _round(xa, policy)
-    new_cache = []
+    new_cache, cross_qk = [], []
     for i in range(dims.n_text_layer):
-        x, c, _ = _block(x, w, f"decoder.blocks.{i}", dims.n_text_head, xa=xa, mask=mask,
-                         kv_cache=kv_cache[i], cross=True, policy=policy)
+        x, c, qk = _block(x, w, f"decoder.blocks.{i}", dims.n_text_head, xa=xa, mask=mask,
+                          kv_cache=kv_cache[i], cross=True, policy=policy)
         new_cache.append(c)
+        cross_qk.append(qk)
     x = _round(_layer_norm(x, w["decoder.ln.weight"], w["decoder.ln.bias"]), policy)
     logits = x @ w["decoder.token_embedding.weight"].T
+    if return_cross_qk:
+        return logits, new_cache, cross_qk
     return logits, new_cache

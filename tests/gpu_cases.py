@@ -696,6 +696,90 @@ def case_transcribe_micro():
     return out
 
 
+def case_word_alignment():
+    """Word-level timestamps (timing.py): cross-attention probabilities of the alignment heads, the normalise / median /
+    head-mean matrix and the DTW path against the oracle, then `transcribe(word_timestamps=True)` end to end."""
+    from oracle import audio as OA, model as OM, timing as OT
+    from whisper_mlx_b200 import timing as T, transcribe
+    from whisper_mlx_b200.tokenizer import get_tokenizer
+
+    out = {}
+    dims, w = _oracle("tiny")
+    m = _product("tiny")
+    tk = get_tokenizer(True, num_languages=m.num_languages, language="en", task="transcribe")
+    mel = torch.from_numpy(OA.log_mel_spectrogram(synth.make_audio("speech", 480000, 11), dims.n_mels))[None]
+    xa = OM.encoder_forward(w, dims, mel, policy="bf16")
+    rng = np.random.default_rng(5)
+    text_tokens = [int(t) for t in rng.integers(300, 20000, size=37)]
+    heads = np.asarray(m.alignment_heads).reshape(-1, 2)
+    for num_frames in (3000, 1724):
+        # ---- oracle: scores -> matrix -> path
+        tokens = torch.tensor([*tk.sot_sequence, tk.no_timestamps, *text_tokens, tk.eot], dtype=torch.long)
+        logits_ref, _, cross_qk = OM.decoder_forward(w, dims, tokens[None], xa, policy="bf16", return_cross_qk=True)
+        mat_ref = OT.alignment_matrix(cross_qk, heads, num_frames)
+        # ---- GPU: probabilities from K8, K12a/b matrix, K12c path
+        n = len(tokens)
+        sess = m.decode_session(1, 1, dims.n_text_ctx, slot=7)
+        sess.load(_bf16(xa).cuda())
+        sess.set_tokens(tokens[None].to(torch.int32))
+        first = int(heads[:, 0].min())
+        logits, probs = sess.forward_full(n, first)
+        torch.cuda.synchronize()
+        lerr = (logits.cpu() - logits_ref[0]).abs().max().item()
+        p_ref = torch.softmax(torch.stack([cross_qk[l][0] for l in range(first, dims.n_text_layer)]).float(), -1)  # (L', H, n, T)
+        perr = (probs[:, 0].permute(0, 2, 1, 3).cpu() - p_ref).abs().max().item()
+        assert abs(probs[:, 0].sum(-1).mean().item() - 1.0) < 1e-3
+        mat = T.alignment_matrix(m, probs, first, num_frames)
+        merr = float(np.abs(mat.cpu().numpy() - mat_ref).max())
+        out[f"f{num_frames}"] = {"logits": lerr, "probs": perr, "matrix": merr}
+        assert lerr <= 6e-2 and perr <= 2e-4 and merr <= 0.1, out  # z-score units; measured 0.019 / 2.7e-5 / 0.032
+        # the matrix stage alone, on the GPU's own probabilities (isolates K12a/b from model rounding): tight
+        fake_qk = [None] * first + [torch.log(probs[i, 0].permute(1, 0, 2).cpu().double())[None] for i in range(probs.shape[0])]
+        mat_same = OT.alignment_matrix(fake_qk, heads, num_frames)
+        m2 = float(np.abs(mat.cpu().numpy() - mat_same).max())
+        out[f"f{num_frames}"]["matrix_same_input"] = m2
+        assert m2 <= 2e-3, m2
+        # DTW: identical path on identical input
+        n_sot = len(tk.sot_sequence)
+        ti, tj = T.dtw(m, mat[n_sot: n - 1])
+        ri, rj = OT.dtw(-mat[n_sot: n - 1].cpu().numpy())
+        assert np.array_equal(ti, ri) and np.array_equal(tj, rj), "DTW path differs"
+        assert ti[0] == 0 and tj[0] == 0 and ti[-1] == len(text_tokens) and tj[-1] == num_frames // 2 - 1
+        # words: same boundaries as the oracle's bookkeeping run on the GPU path
+        words = T.find_alignment(m, tk, text_tokens, _bf16(xa).cuda(), num_frames)
+        assert len(words) >= 1 and all(0.0 <= wd.start <= wd.end <= num_frames / 100 + 1e-6 for wd in words)
+        assert [t for wd in words for t in wd.tokens] == text_tokens  # the trailing EOT "word" is dropped by the zip
+        assert all(0.0 <= wd.probability <= 1.0 for wd in words)
+        out[f"f{num_frames}"]["n_words"] = len(words)
+    # ---- end to end: every segment carries its words, monotonic and inside the file
+    mm = _product("micro")
+    audio = synth.long_audio(50.0, 3)
+    for hst in (None, 2.0):
+        r = transcribe(audio, model=mm, temperature=0.0, language="en", sample_len=24, word_timestamps=True,
+                       condition_on_previous_text=False, hallucination_silence_threshold=hst,
+                       logprob_threshold=None, compression_ratio_threshold=None, no_speech_threshold=None)
+        # (with random weights every word is improbable: the hallucination filter may drop all segments)
+        assert (len(r["segments"]) >= 1 or hst is not None) and all("words" in s for s in r["segments"])
+        n_words = 0
+        for s in r["segments"]:
+            last = -1.0
+            for wd in s["words"]:
+                assert wd["start"] <= wd["end"] and wd["end"] <= 51.0 and wd["start"] >= last - 1e-6, (s["id"], wd)
+                last = wd["start"]
+                n_words += 1
+        # words are handed out by token counts, so one may straddle a segment boundary: compare per window
+        for seek in sorted({s["seek"] for s in r["segments"]}):
+            if seek > 5000 - 4:
+                continue  # a tail window of a single attention frame carries no words (timing.py guard)
+            segs = [s for s in r["segments"] if s["seek"] == seek]
+            joined_words = "".join(wd["word"] for s in segs for wd in s["words"])
+            joined_text = "".join(s["text"] for s in segs)
+            assert joined_words.replace(" ", "") == joined_text.replace(" ", ""), (seek, joined_words, joined_text)
+        out[f"transcribe_hst{hst}"] = (len(r["segments"]), n_words)
+        assert n_words >= 1 or hst is not None
+    return out
+
+
 CASES = {
     "logmel_noise": case_logmel_noise,
     "logmel_kinds": case_logmel_kinds,
@@ -715,4 +799,5 @@ CASES = {
     "large_v3_parity": case_large_v3_parity,
     "decode_dual_stream": case_decode_dual_stream,
     "transcribe_micro": case_transcribe_micro,
+    "word_alignment": case_word_alignment,
 }

@@ -120,7 +120,7 @@ def test_segmentation_matches_oracle(fixed):
     for s in streams:
         res = DecodingResult(audio_features=None, language="en", tokens=s, avg_logprob=-0.5, no_speech_prob=0.0, temperature=0.0,
                              compression_ratio=1.0)
-        segs, adv = _segments_for_window(np.array(s, dtype=np.int64), 3000, 3000, res, tk, 2, 0.02, not fixed)
+        segs, adv, _ = _segments_for_window(np.array(s, dtype=np.int64), 3000, 3000, res, tk, 2, 0.02, not fixed)
         ref, ref_adv = _oracle_segments(s, 3000, 3000, fixed)
         assert adv == ref_adv, s
         assert len(segs) == len(ref)
@@ -256,3 +256,52 @@ def test_mlx_dequantize(bits, group_size):
     assert set(d) == {"a.weight", "b.weight"} and d["a.weight"].shape == w.shape
     with pytest.raises(NotImplementedError):
         dequantize(words, scales, biases, group_size, 3)
+
+
+def test_word_distribution_matches_oracle():
+    """The host half of timing.py (punctuation merging, duration heuristics, words -> segments, boundary reconciliation)
+    against the oracle restatement, on synthetic alignments that hit every branch."""
+    import copy
+    import random
+
+    from oracle import timing as OT
+    from whisper_mlx_b200 import timing as T
+    from whisper_mlx_b200.transcribe import _get_end, _is_segment_anomaly, _next_words_segment, _word_anomaly_score
+
+    eot = 50257
+    rnd = random.Random(7)
+    vocab = [" hello", " world", ",", ".", " (", ")", " it", "'s", " a", " -", " test", "?", " “", "”", " long"]
+    for trial in range(40):
+        n = rnd.randint(1, 14)
+        t = 0.0
+        ali, tok = [], 1000
+        for i in range(n):
+            dur = rnd.choice([0.0, 0.08, 0.2, 0.3, 0.5, 2.6])
+            word = rnd.choice(vocab)
+            k = rnd.randint(1, 3)
+            ali.append((word, list(range(tok, tok + k)), round(t, 2), round(t + dur, 2), rnd.random()))
+            tok += k
+            t += dur + rnd.choice([0.0, 0.1, 1.5])
+        ali.append(("", [eot], round(t, 2), round(t, 2), 0.0))
+        all_tokens = [x for a in ali[:-1] for x in a[1]]
+        cut = rnd.randint(0, len(all_tokens))
+        seek = rnd.choice([0, 3000, 4500])
+        segments = [{"seek": seek, "start": seek / 100 + 0.0, "end": seek / 100 + t / 2, "tokens": [50365] + all_tokens[:cut] + [50400]},
+                    {"seek": seek, "start": seek / 100 + t / 2, "end": seek / 100 + t + 0.7, "tokens": all_tokens[cut:]}]
+        last = rnd.choice([0.0, seek / 100 - 3.0, seek / 100])
+        s1, s2 = copy.deepcopy(segments), copy.deepcopy(segments)
+        a1 = [T.WordTiming(*a) for a in copy.deepcopy(ali)]
+        a2 = [OT.WordTiming(*a) for a in copy.deepcopy(ali)]
+        kw = dict(eot=eot, prepend_punctuations="\"'“¿([{-", append_punctuations="\"'.。,，!！?？:：”)]}、", last_speech_timestamp=last)
+        r1 = T.distribute_words(segments=s1, alignment=a1, **kw)
+        r2 = OT.add_word_timestamps(segments=s2, alignment=a2, **kw)
+        assert r1 == r2 and s1 == s2, trial
+        assert [w.word for w in a1] == [w.word for w in a2]
+        assert _get_end(s1) == next((w["end"] for s in reversed(s1) for w in reversed(s["words"])), s1[-1]["end"])
+    # anomaly scoring (transcribe.py helpers of the hallucination filter)
+    assert _word_anomaly_score({"word": "a", "start": 0.0, "end": 0.05, "probability": 0.1}) == pytest.approx(1.0 + (0.133 - 0.05) * 15)
+    assert _word_anomaly_score({"word": "a", "start": 0.0, "end": 3.0, "probability": 0.9}) == pytest.approx(1.0)
+    good = {"words": [{"word": " ok", "start": 0.0, "end": 0.3, "probability": 0.9}] * 4}
+    bad = {"words": [{"word": " uh", "start": 0.0, "end": 0.02, "probability": 0.05}] * 4}
+    assert not _is_segment_anomaly(good) and _is_segment_anomaly(bad) and not _is_segment_anomaly(None)
+    assert _next_words_segment([{"words": []}, good]) is good and _next_words_segment([{"words": []}]) is None

@@ -98,6 +98,9 @@ SIGNATURES = {
     "b200w_cross_kv": (i32, [vp, vp, i32, vp, i64, i32, vp]),
     "b200w_decoder_workspace_bytes": (sz, [vp, i32, i32]),
     "b200w_decoder_step": (i32, [vp, C.POINTER(DecodeState), i32, i32, i32, C.POINTER(FilterParams), vp, sz, vp]),
+    "b200w_decoder_forward_full": (i32, [vp, C.POINTER(DecodeState), i32, vp, sz, vp, vp, i32, vp]),
+    "b200w_alignment_matrix": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, vp]),
+    "b200w_dtw": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
 }
 
 

@@ -776,4 +776,84 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   return kOk;
 }
 
+int b200w_decoder_forward_full(const b200w_model* mp, const b200w_decode_state* st, int n_q, void* workspace,
+                               size_t workspace_bytes, float* logits_all, float* cross_probs, int probs_first_layer,
+                               void* stream_) {
+  B200W_CHECK_ARG(mp && st && workspace && n_q > 0, "decoder_forward_full: bad arguments");
+  const Model& m = mp->m;
+  const b200w_dims& dm = m.w.dims;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int d = dm.n_text_state, H = dm.n_text_head, T = dm.n_audio_ctx, B = st->n_seq;
+  const int rows = B * n_q;
+  B200W_CHECK_ARG(B > 0 && probs_first_layer >= 0 && probs_first_layer <= dm.n_text_layer, "decoder_forward_full: bad sizes");
+  Carver c(workspace, workspace_bytes);
+  DecBufs bf;
+  if (carve_decoder(dm, B, n_q, c, &bf) > workspace_bytes) {
+    set_last_error("decoder_forward_full: workspace too small (%zu < %zu)", workspace_bytes, c.off);
+    return kErrWorkspace;
+  }
+  float* x = static_cast<float*>(bf.x);
+  B200W_TRY(launch_embed(st->tokens, st->tokens_ld, st->pos, B, n_q, (const __nv_bfloat16*)m.w.tok_emb,
+                         (const __nv_bfloat16*)m.w.dec_pos, d, dm.n_text_ctx, x, stream));
+  const size_t probs_layer = (size_t)B * n_q * H * T;
+  for (int l = 0; l < dm.n_text_layer; ++l) {
+    const b200w_dec_layer& L = m.dec[l];
+    __nv_bfloat16* kp = static_cast<__nv_bfloat16*>(st->k_pages) + (size_t)l * st->layer_page_stride;
+    __nv_bfloat16* vp = static_cast<__nv_bfloat16*>(st->v_pages) + (size_t)l * st->layer_page_stride;
+    const __nv_bfloat16* ckv = static_cast<const __nv_bfloat16*>(st->cross_kv) + (size_t)l * st->cross_layer_stride;
+    float* probs = (cross_probs != nullptr && l >= probs_first_layer) ? cross_probs + (size_t)(l - probs_first_layer) * probs_layer
+                                                                     : nullptr;
+    B200W_TRY(launch_layernorm(x, L.attn_ln_g, L.attn_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_qkv, 3 * d, d, bf.qkv, 3 * d, false, L.b_qkv, false, nullptr, 0, 0, stream));
+    B200W_TRY(launch_decoder_self_attention((const __nv_bfloat16*)bf.qkv, B, n_q, H, st->pos, kp, vp, st->block_table,
+                                            st->max_pages, st->page_size, (__nv_bfloat16*)bf.att, stream));
+    B200W_TRY(gemm(bf.att, d, rows, L.w_out, d, d, x, d, true, L.b_out, false, x, d, 0, stream));
+    B200W_TRY(launch_layernorm(x, L.cross_ln_g, L.cross_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_cq, d, d, bf.qc, d, false, L.b_cq, false, nullptr, 0, 0, stream));
+    B200W_TRY(launch_decoder_cross_attention((const __nv_bfloat16*)bf.qc, B, n_q, H, ckv, (long long)T * 2 * d, T,
+                                             st->cross_slot, (__nv_bfloat16*)bf.att, stream, nullptr, 0, 0, nullptr, nullptr,
+                                             probs));
+    B200W_TRY(gemm(bf.att, d, rows, L.w_cout, d, d, x, d, true, L.b_cout, false, x, d, 0, stream));
+    B200W_TRY(launch_layernorm(x, L.mlp_ln_g, L.mlp_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+    B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));
+    B200W_TRY(gemm(bf.mlp, 4 * d, rows, L.w_mlp2, d, 4 * d, x, d, true, L.b_mlp2, false, x, d, 0, stream));
+  }
+  if (logits_all != nullptr) {
+    B200W_CHECK_ARG(st->logits_ld >= ((dm.n_vocab + 127) / 128) * 128, "decoder_forward_full: logits_ld too small");
+    B200W_TRY(launch_layernorm(x, m.w.dec_ln_g, m.w.dec_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
+    GemmParams p{};
+    p.n_batch = 1;
+    p.rows_per_batch = rows;
+    p.N = dm.n_vocab;
+    p.K = d;
+    p.n_store = dm.n_vocab;
+    p.ldc = st->logits_ld;
+    p.out_f32 = 1;
+    p.out = logits_all;
+    p.tag = "dec_gemm_logits_all";
+    const int bn = 128;
+    CUtensorMap ta, tb;
+    B200W_TRY(make_tmap_w(&tb, m.w.tok_emb, dm.n_vocab, d, bn));
+    B200W_TRY(make_tmap_a(&ta, bf.h, 1, rows, d, d, (long long)rows * d));
+    B200W_TRY(launch_gemm(ta, tb, p, bn, stream));
+  }
+  return kOk;
+}
+
+int b200w_alignment_matrix(const float* cross_probs, int n_layers_stored, int n_seq, int seq, int n_q, int n_head,
+                           int n_ctx, const int* heads, int n_sel, int n_frames, float* stats, float* matrix,
+                           void* stream) {
+  B200W_CHECK_ARG(cross_probs && heads && stats && matrix && n_layers_stored > 0 && seq >= 0 && seq < n_seq,
+                  "alignment_matrix: bad arguments");
+  const long long layer_stride = (long long)n_seq * n_q * n_head * n_ctx;
+  return launch_alignment_matrix(cross_probs, layer_stride, (long long)seq * n_q * n_head * n_ctx, n_q, n_head, n_ctx, heads,
+                                 n_sel, n_frames, stats, matrix, (cudaStream_t)stream);
+}
+
+int b200w_dtw(const float* matrix, long long ld, int N, int M, float* cost, signed char* trace, int* text_idx,
+              int* time_idx, int* path_len, void* stream) {
+  B200W_CHECK_ARG(matrix && cost && trace && text_idx && time_idx && path_len, "dtw: null pointer");
+  return launch_dtw(matrix, ld, N, M, cost, trace, text_idx, time_idx, path_len, (cudaStream_t)stream);
+}
+
 }  // extern "C"

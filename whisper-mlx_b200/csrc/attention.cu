@@ -477,12 +477,17 @@ constexpr int kMaxCrossKeys = 1536;
 // (registers 48 / 56 / 64 / 96 / 128 cut the resident CTAs); prefetching V across the softmax barriers: 176.
 constexpr int kCrossUnroll = B200W_CROSS_UNROLL;
 
+// kProbs: also store the attention probabilities (f32, [b][qi][h][T]) -- the cross-attention weights the word-level
+// alignment reads (UPSTREAM timing.py: softmax of the captured QK).  A separate instantiation: the decode-step
+// kernel is sensitive to every extra instruction in its prologue (section on kCrossUnroll above).
+template <bool kProbs>
 __global__ void __launch_bounds__(kCrossThreads)
 decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int n_head,
                                const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride, int T,
                                const int* __restrict__ slot, __nv_bfloat16* __restrict__ out,
                                const float* __restrict__ part, int n_split, long long split_stride,
-                               const float* __restrict__ bias, const int* __restrict__ finished) {
+                               const float* __restrict__ bias, const int* __restrict__ finished,
+                               float* __restrict__ probs_out) {
   __shared__ float s_p[kMaxCrossKeys];
   __shared__ float s_red[kCrossWarps];
   __shared__ float s_part[kCrossWarps][kHd];
@@ -573,6 +578,12 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   sum = 0.0f;
 #pragma unroll
   for (int i = 0; i < kCrossWarps; ++i) sum += s_red[i];
+  if constexpr (kProbs) {
+    // each thread re-reads the entries it wrote itself (same j = tid + k * kCrossThreads mapping): no barrier needed
+    float* po = probs_out + (((long long)b * n_q + qi) * n_head + h) * T;
+    const float inv = 1.0f / sum;
+    for (int j = tid; j < T; j += kCrossThreads) po[j] = s_p[j] * inv;
+  }
 
   // ---- output ----
   float acc[8];
@@ -622,14 +633,19 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
 int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, int n_head,
                                    const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
                                    __nv_bfloat16* out, cudaStream_t stream, const float* part, int n_split,
-                                   long long split_stride, const float* bias, const int* finished) {
+                                   long long split_stride, const float* bias, const int* finished, float* probs_out) {
   B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "cross_attention: bad sizes");
   B200W_CHECK_ARG(n_split > 0 ? (part && bias) : (q != nullptr), "cross_attention: missing query input");
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
   dim3 grid(n_head, n_seq, n_q);
   ProfScope prof_("decoder_cross_attention", stream);
-  B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head, cross_kv,
-                         seq_stride, T, slot, out, part, n_split, split_stride, bias, finished));
+  if (probs_out != nullptr)
+    B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel<true>, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head,
+                           cross_kv, seq_stride, T, slot, out, part, n_split, split_stride, bias, finished, probs_out));
+  else
+    B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel<false>, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head,
+                           cross_kv, seq_stride, T, slot, out, part, n_split, split_stride, bias, finished,
+                           static_cast<float*>(nullptr)));
   count_launch();
   return kOk;
 }

@@ -128,6 +128,14 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
                                    const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
                                    __nv_bfloat16* out, cudaStream_t stream, const float* part = nullptr,
                                    int n_split = 0, long long split_stride = 0, const float* bias = nullptr,
-                                   const int* finished = nullptr);
+                                   const int* finished = nullptr, float* probs_out = nullptr);
+
+// ---------------------------------------------------------------------------------------- K12 word alignment
+// stats workspace: (2 * n_sel * n_frames + n_sel * n_tok) floats; heads: n_sel (layer-relative index, head) pairs
+int launch_alignment_matrix(const float* probs, long long layer_stride, long long seq_off, int n_tok, int n_head, int T,
+                            const int* heads, int n_sel, int n_frames, float* stats, float* matrix, cudaStream_t stream);
+// cost: (N + 1) * (M + 1) floats, trace: as many bytes; text_idx / time_idx: N + M ints, written back to front
+int launch_dtw(const float* matrix, long long ld, int N, int M, float* cost, signed char* trace, int* text_idx,
+               int* time_idx, int* path_len, cudaStream_t stream);
 
 }  // namespace b200w

@@ -123,7 +123,7 @@ class DecodeSession:
         self.logits = torch.empty((B, ld), dtype=torch.float32, device=dev)
         self.logits_aux = torch.empty((B, ld), dtype=torch.float32, device=dev)
         self.suppress_bits = torch.zeros((dm.n_vocab + 31) // 32, dtype=torch.int32, device=dev)
-        self._ws: Dict[int, torch.Tensor] = {}
+        self._ws: Dict[Union[int, str], torch.Tensor] = {}
         self._graphs: Dict[bytes, Tuple[torch.cuda.CUDAGraph, int]] = {}  # keyed by the filter parameters baked in
         self._fp = _lib.FilterParams()
         self.state = _lib.DecodeState(
@@ -179,6 +179,24 @@ class DecodeSession:
 
     def aux_logits(self) -> torch.Tensor:
         return self.logits_aux
+
+    def forward_full(self, n_q: int, probs_first_layer: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Teacher forcing over the n_q loaded tokens with everything word-level alignment needs: the logits of every
+        position, (n_seq * n_q, n_vocab) f32, and the cross-attention probabilities of the layers >= probs_first_layer,
+        (layers, n_seq, n_q, n_head, 1500) f32 (the decoder half of UPSTREAM Whisper.forward_with_cross_qk)."""
+        dm = self.model.dims
+        dev = self.model.device
+        n_layers = dm.n_text_layer - probs_first_layer
+        logits = torch.empty((self.n_seq * n_q, self.model.logits_ld), dtype=torch.float32, device=dev)
+        probs = torch.empty((n_layers, self.n_seq, n_q, dm.n_text_head, dm.n_audio_ctx), dtype=torch.float32, device=dev)
+        if "full" not in self._ws:  # one buffer for every sequence length (short sequences also carve split-K slabs)
+            nbytes = max(self.lib.b200w_decoder_workspace_bytes(self.model._handle, self.n_seq, q) for q in (1, dm.n_text_ctx))
+            self._ws["full"] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = self._ws["full"]
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.b200w_decoder_forward_full(self.model._handle, C.byref(self.state), n_q, _lib.ptr(ws), ws.numel(),
+                                                           _lib.ptr(logits), _lib.ptr(probs), probs_first_layer, _lib.stream()))
+        return logits[:, : dm.n_vocab], probs
 
     def prompt_step(self, n_q: int, sot_index: int) -> None:
         with torch.cuda.device(self.model.device):

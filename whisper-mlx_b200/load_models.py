@@ -77,8 +77,10 @@ def load_model(path_or_hf_repo: str, dtype: torch.dtype = torch.bfloat16, device
     weights = _read_weights(model_path)
     if quantization is not None:  # MLX-quantised checkpoint (e.g. the 4-bit mlx-community variants): expand at load
         weights = dequantize_weights(weights, int(quantization.get("group_size", 64)), int(quantization.get("bits", 4)))
-    weights.pop("alignment_heads", None)
+    alignment_heads = weights.pop("alignment_heads", None)
     weights = {k: v for k, v in weights.items() if not k.endswith("encoder.positional_embedding")}
     model = Whisper(model_args, weights, device=device, dtype=dtype)
+    if alignment_heads is not None:  # (n, 2) [layer, head] pairs used by word-level timestamps
+        model.alignment_heads = np.asarray(alignment_heads.cpu().numpy(), dtype=np.int64).reshape(-1, 2)
     model.model_path = str(model_path)
     return model

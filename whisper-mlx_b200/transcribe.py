@@ -25,6 +25,7 @@ from .audio import FRAMES_PER_SECOND, HOP_LENGTH, N_FRAMES, N_SAMPLES, SAMPLE_RA
 from .decoding import DecodingOptions, DecodingResult, DecodingTask, detect_language
 from .load_models import load_model
 from .sharding import gather_by_index, plan_windows, shard_indices
+from .timing import add_word_timestamps
 from .tokenizer import LANGUAGES, get_tokenizer
 
 
@@ -53,6 +54,40 @@ class ModelHolder:
             cls.model = load_model(model_path, dtype=dtype)
             cls.model_path = model_path
         return cls.model
+
+
+_PUNCTUATION = "\"'“¿([{-\"'.。,，!！?？:：”)]}、"
+
+
+def _word_anomaly_score(word: dict) -> float:
+    probability = word.get("probability", 0.0)
+    duration = word["end"] - word["start"]
+    score = 0.0
+    if probability < 0.15:
+        score += 1.0
+    if duration < 0.133:
+        score += (0.133 - duration) * 15
+    if duration > 2.0:
+        score += duration - 2.0
+    return score
+
+
+def _is_segment_anomaly(segment: Optional[dict]) -> bool:
+    if segment is None or not segment["words"]:
+        return False
+    words = [w for w in segment["words"] if w["word"] not in _PUNCTUATION]
+    words = words[:8]
+    score = sum(_word_anomaly_score(w) for w in words)
+    return score >= 3 or score + 0.01 >= len(words)
+
+
+def _next_words_segment(segments: List[dict]) -> Optional[dict]:
+    return next((s for s in segments if s["words"]), None)
+
+
+def _get_end(segments: List[dict]) -> Optional[float]:
+    return next((w["end"] for s in reversed(segments) for w in reversed(s["words"])),
+                segments[-1]["end"] if segments else None)
 
 
 def _segments_for_window(tokens: np.ndarray, seek: int, segment_size: int, result: DecodingResult, tokenizer,
@@ -107,7 +142,7 @@ def _segments_for_window(tokens: np.ndarray, seek: int, segment_size: int, resul
         if segment["start"] == segment["end"] or segment["text"].strip() == "":
             segment["text"] = ""
             segment["tokens"] = []
-    return current_segments, advance
+    return current_segments, advance, single_timestamp_ending
 
 
 def transcribe(
@@ -143,9 +178,9 @@ def transcribe(
     decode only its block of windows and gather the per-window segments on the host, so every rank returns
     the full result.
     """
-    if word_timestamps:
-        raise NotImplementedError("word_timestamps is not implemented yet (it is not on the `./run` path)")
-    if hallucination_silence_threshold is not None and verbose:
+    if word_timestamps and decode_options.get("task", "transcribe") == "translate" and verbose:
+        warnings.warn("Word-level timestamps on translations may not be reliable.")
+    if hallucination_silence_threshold is not None and not word_timestamps and verbose:
         warnings.warn("--hallucination_silence_threshold requires --word_timestamps True; it has no effect")
 
     dtype = torch.bfloat16 if decode_options.get("fp16", True) else torch.float32
@@ -238,6 +273,7 @@ def transcribe(
     all_tokens: List[int] = []
     all_segments: List[dict] = []
     prompt_reset_since = 0
+    last_speech_timestamp = 0.0
     if initial_prompt is not None:
         initial_prompt_tokens = tokenizer.encode(" " + initial_prompt.strip())
         all_tokens.extend(initial_prompt_tokens)
@@ -259,7 +295,7 @@ def transcribe(
         all_segments.extend({"id": i, **segment} for i, segment in enumerate(current_segments, start=len(all_segments)))
         all_tokens.extend(token for segment in current_segments for token in segment["tokens"])
 
-    batched = window_batch > 0 and not condition_on_previous_text and initial_prompt is None
+    batched = window_batch > 0 and not condition_on_previous_text and initial_prompt is None and not word_timestamps
     if world_size > 1 and not batched:
         raise ValueError("sharding over ranks needs the fixed-window mode (window_batch > 0, "
                          "condition_on_previous_text=False, no initial_prompt): exact mode is sequential per file")
@@ -285,7 +321,7 @@ def transcribe(
                     local[i] = None
                     continue
                 tokens = np.array(res.tokens, dtype=np.int64)
-                segs, _ = _segments_for_window(tokens, seek, size, res, tokenizer, input_stride, time_precision, False)
+                segs, _, _ = _segments_for_window(tokens, seek, size, res, tokenizer, input_stride, time_precision, False)
                 local[i] = segs
         # host-side gather of the per-window segments (no device collective on the data path)
         for segs in gather_by_index(local, len(windows)) if world_size > 1 else [local[i] for i in range(len(windows))]:
@@ -311,9 +347,72 @@ def transcribe(
             if should_skip(result):
                 seek += segment_size  # fast-forward to the next segment boundary
                 continue
-            segs, advance = _segments_for_window(tokens, seek, segment_size, result, tokenizer, input_stride,
-                                                 time_precision, True)
+            previous_seek = seek
+            time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
+            window_end_time = float((seek + N_FRAMES) * HOP_LENGTH / SAMPLE_RATE)
+            segment_duration = segment_size * HOP_LENGTH / SAMPLE_RATE
+            segs, advance, single_timestamp_ending = _segments_for_window(tokens, seek, segment_size, result, tokenizer,
+                                                                          input_stride, time_precision, True)
             seek += advance
+            if word_timestamps:
+                last_speech_timestamp = add_word_timestamps(
+                    segments=segs, model=model, tokenizer=tokenizer, features=features, num_frames=segment_size,
+                    prepend_punctuations=prepend_punctuations, append_punctuations=append_punctuations,
+                    last_speech_timestamp=last_speech_timestamp)
+                if not single_timestamp_ending:
+                    last_word_end = _get_end(segs)
+                    if last_word_end is not None and last_word_end > time_offset:
+                        seek = round(last_word_end * FRAMES_PER_SECOND)
+                # skip silence before possible hallucinations
+                if hallucination_silence_threshold is not None:
+                    threshold = hallucination_silence_threshold
+                    if not single_timestamp_ending:
+                        last_word_end = _get_end(segs)
+                        if last_word_end is not None and last_word_end > time_offset:
+                            remaining_duration = window_end_time - last_word_end
+                            if remaining_duration > threshold:
+                                seek = round(last_word_end * FRAMES_PER_SECOND)
+                            else:
+                                seek = previous_seek + segment_size
+                    # if the first segment might be a hallucination, skip the leading silence
+                    first_segment = _next_words_segment(segs)
+                    if first_segment is not None and _is_segment_anomaly(first_segment):
+                        gap = first_segment["start"] - time_offset
+                        if gap > threshold:
+                            seek = previous_seek + round(gap * FRAMES_PER_SECOND)
+                            continue
+                    # skip silence before any possible hallucination that is surrounded by silence or more hallucinations
+                    hal_last_end = last_speech_timestamp
+                    for si in range(len(segs)):
+                        segment = segs[si]
+                        if not segment["words"]:
+                            continue
+                        if _is_segment_anomaly(segment):
+                            next_segment = _next_words_segment(segs[si + 1:])
+                            if next_segment is not None:
+                                hal_next_start = next_segment["words"][0]["start"]
+                            else:
+                                hal_next_start = time_offset + segment_duration
+                            silence_before = (segment["start"] - hal_last_end > threshold or segment["start"] < threshold
+                                              or segment["start"] - time_offset < 2.0)
+                            silence_after = (hal_next_start - segment["end"] > threshold or _is_segment_anomaly(next_segment)
+                                             or window_end_time - segment["end"] < 2.0)
+                            if silence_before and silence_after:
+                                seek = round(max(time_offset + 1, segment["start"]) * FRAMES_PER_SECOND)
+                                if content_duration - segment["end"] < threshold:
+                                    seek = content_frames
+                                segs[si:] = []
+                                break
+                        hal_last_end = segment["end"]
+                last_word_end = _get_end(segs)
+                if last_word_end is not None:
+                    last_speech_timestamp = last_word_end
+                # the reference clears instantaneous / empty segments after the word pass
+                for segment in segs:
+                    if segment["start"] == segment["end"] or segment["text"].strip() == "":
+                        segment["text"] = ""
+                        segment["tokens"] = []
+                        segment["words"] = []
             emit(segs)
             if not condition_on_previous_text or result.temperature > 0.5:
                 # do not feed the prompt tokens if a high temperature was used
