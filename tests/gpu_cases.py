@@ -650,6 +650,79 @@ def case_large_v3_parity():
     return out
 
 
+def _config_decode_case(name: str, batch: int, n_steps: int):
+    """A BASELINE decode configuration at its full batch size: greedy decode of `batch` windows of which only four are
+    distinct.  Size-independent properties: every copy decodes exactly like its original (rows of a batch never
+    interact), and the four originals follow the oracle's tokens."""
+    from oracle import decoding as OD, model as OM
+    from whisper_mlx_b200.decoding import DecodingOptions, DecodingTask
+    from whisper_mlx_b200.whisper import ModelDimensions, Whisper
+
+    dims_d = synth.DIMS[name]
+    weights = dict(synth.random_weights(dims_d, 0, device="cuda"))
+    m = Whisper(ModelDimensions(**dims_d), weights)
+    w32 = {k: v.detach().to("cpu", torch.float32) for k, v in weights.items() if k.startswith("decoder.")}
+    del weights
+    dims = OM.ModelDimensions(**dims_d)
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(11)
+    base = _bf16(torch.randn(4, dims.n_audio_ctx, dims.n_audio_state, generator=g))
+    xa = base[torch.arange(batch) % 4].cuda()
+    got = DecodingTask(m, DecodingOptions(language="en", sample_len=n_steps)).run_features(xa)
+    assert len(got) == batch
+    for i in range(4, batch):
+        assert got[i].tokens == got[i % 4].tokens and got[i].avg_logprob == got[i % 4].avg_logprob, (i, "copy differs")
+        assert got[i].no_speech_prob == got[i % 4].no_speech_prob
+    ref = OD.decode(w32, dims, torch.zeros(4, 3000, dims.n_mels), language="en", sample_len=n_steps, policy="bf16",
+                    audio_features=base.float())
+    out = {"batch": batch}
+    total = full = 0
+    for i in range(4):
+        k = 0
+        while k < min(len(got[i].tokens), len(ref[i].tokens)) and got[i].tokens[k] == ref[i].tokens[k]:
+            k += 1
+        out[f"w{i}_prefix"] = (k, len(ref[i].tokens))
+        total += k
+        full += len(ref[i].tokens)
+        assert abs(got[i].no_speech_prob - ref[i].no_speech_prob) <= 0.05 * max(ref[i].no_speech_prob, 1e-6) + 1e-7
+    assert total >= 0.5 * full, out  # a near-tie flipped by rounding ends the comparable prefix (cf. decode_tiny)
+    return out
+
+
+def case_config2_logmel_batch1024():
+    """BASELINE configs[1]: the log-mel front-end on 1024 x 30 s windows, 80 and 128 mel bins.  Four distinct signals are
+    tiled over the batch: every copy must equal its original bit for bit (tiles never interact, each row has its own
+    clamp maximum) and the originals must match the oracle."""
+    from oracle import audio as OA
+    from whisper_mlx_b200.audio import log_mel_spectrogram
+
+    base = np.stack([synth.white_noise(480000, 0), 0.01 * synth.white_noise(480000, 1), synth.make_audio("speech", 480000, 2),
+                     synth.make_audio("tones", 480000, 3)]).astype(np.float32)
+    x = torch.from_numpy(base).cuda()[torch.arange(1024, device="cuda") % 4].contiguous()
+    out = {}
+    for n_mels in (80, 128):
+        got = log_mel_spectrogram(x, n_mels=n_mels)
+        assert got.shape == (1024, 3000, n_mels)
+        assert torch.equal(got[4:], got[:4].repeat(255, 1, 1)), "a copy differs from its original"
+        for i in range(4):
+            ref = OA.log_mel_spectrogram(base[i], n_mels)
+            e = float((np.abs(got[i].cpu().numpy() - ref) / np.maximum(1.0, np.abs(ref))).max())
+            out[f"mel{n_mels}_w{i}"] = e
+            assert e <= (1e-3 if i == 3 else LOGMEL_TOL), (n_mels, i, e)
+        del got
+    return out
+
+
+def case_config3_small_batch64():
+    """BASELINE configs[2]: whisper-small greedy decode, batch 64 (split-K chain path: rows <= 128)."""
+    return _config_decode_case("small", 64, 24)
+
+
+def case_config5_turbo_batch256():
+    """BASELINE configs[4]: whisper-large-v3-turbo (4-layer decoder), batch 256 (general path: rows > 128)."""
+    return _config_decode_case("large-v3-turbo", 256, 16)
+
+
 def case_decode_dual_stream():
     """Batches of >= 16 windows decode as two half-batches on two streams; the result must not depend on it."""
     from whisper_mlx_b200.decoding import DecodingOptions, DecodingTask
@@ -800,4 +873,7 @@ CASES = {
     "decode_dual_stream": case_decode_dual_stream,
     "transcribe_micro": case_transcribe_micro,
     "word_alignment": case_word_alignment,
+    "config2_logmel_batch1024": case_config2_logmel_batch1024,
+    "config3_small_batch64": case_config3_small_batch64,
+    "config5_turbo_batch256": case_config5_turbo_batch256,
 }
