@@ -20,9 +20,13 @@ constexpr int kHd = 64;
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float fast_exp2(float x) {
+#ifdef B200W_EXP_PROBE  // timing probe only: how much of K6 is the MUFU pipe?
+  return x * 0.001f;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 // descriptor for an MN-major or K-major SW128 tile with explicit leading byte offset
@@ -37,45 +41,62 @@ __device__ __forceinline__ uint64_t make_sw128_desc_lbo(uint32_t smem_addr, uint
 }
 
 // =============================================================================================== K6
+// Template on the key block: BKV = 128 (2 CTAs per SM: 80 KB of tiles, 256 TMEM columns, the 128-wide score row in
+// registers) or BKV = 64 (48 KB, 128 TMEM columns, 64-wide score row: up to 4 CTAs per SM).  Every stage of a key block
+// is serialised inside a CTA (S MMA -> TMEM read -> exp -> P store -> PV MMA -> TMEM read), so the SM is kept busy by
+// CTA-level overlap: more, smaller CTAs hide the MMA / TMEM round trips of each other.
 constexpr int kEncThreads = 128;
 constexpr int kBQ = 128;
-constexpr int kBKV = 128;
-constexpr int kTileBytes = 128 * kHd * 2;  // 16 KB: 128 rows x 128 B
-constexpr int kEncSmem = 3 * kTileBytes + 2 * kTileBytes + 1024 + 128;
+constexpr int kQTileBytes = kBQ * kHd * 2;  // 16 KB: 128 rows x 128 B
 
-__global__ void __launch_bounds__(kEncThreads, 2)
-encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, int T, int d, __nv_bfloat16* __restrict__ out) {
+template <int BKV>
+struct EncCfg {
+  static constexpr int kKvTileBytes = BKV * kHd * 2;   // K or V tile: BKV rows x 128 B
+  static constexpr int kPTileBytes = kBQ * BKV * 2;    // P: BKV / 64 K-major sub-tiles of 128 rows x 128 B
+  static constexpr int kSmem = kQTileBytes + 4 * kKvTileBytes + kPTileBytes + 1024 + 128;  // K and V double-buffered
+  static constexpr int kTmemCols = (BKV + kHd <= 128) ? 128 : 256;  // S (BKV) + O (64), power of two
+  static constexpr int kCtasPerSm = (BKV == 64) ? 3 : 2;  // shared memory: 3 x 65 KB / 2 x 113 KB
+};
+
+template <int BKV>
+__global__ void __launch_bounds__(kEncThreads, EncCfg<BKV>::kCtasPerSm)
+encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int T, int d,
+                         __nv_bfloat16* __restrict__ out) {
+  using Cfg = EncCfg<BKV>;
   extern __shared__ unsigned char att_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* sQ = smem;
-  unsigned char* sK = smem + kTileBytes;
-  unsigned char* sV = smem + 2 * kTileBytes;
-  unsigned char* sP = smem + 3 * kTileBytes;  // two 16 KB K-major sub-tiles (keys 0-63, 64-127)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
+  unsigned char* sK = sQ + kQTileBytes;             // two K tiles (block j lives in buffer j & 1)
+  unsigned char* sV = sK + 2 * Cfg::kKvTileBytes;   // two V tiles
+  unsigned char* sP = sV + 2 * Cfg::kKvTileBytes;   // BKV / 64 K-major sub-tiles (keys 0-63, 64-127) of 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPTileBytes);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;
-  uint64_t* bar_v = bars + 2;
-  uint64_t* bar_s = bars + 3;
-  uint64_t* bar_o = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_k = bars + 1;  // [2]
+  uint64_t* bar_v = bars + 3;  // [2]
+  uint64_t* bar_s = bars + 5;
+  uint64_t* bar_o = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
-  const int nkv = (T + kBKV - 1) / kBKV;
+  const int nkv = (T + BKV - 1) / BKV;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
     mbar_init(bar_q, 1);
-    mbar_init(bar_k, 1);
-    mbar_init(bar_v, 1);
+    mbar_init(&bar_k[0], 1);
+    mbar_init(&bar_k[1], 1);
+    mbar_init(&bar_v[0], 1);
+    mbar_init(&bar_v[1], 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
     fence_barrier_init();
   }
   __syncwarp();
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
   tcgen05_fence_before();
@@ -83,150 +104,203 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_qkv, int T, int 
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t tmem_o = tmem_s + 128;
+  const uint32_t tmem_o = tmem_s + BKV;
   pdl_wait();
   pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
 
+  // K / V tiles are requested two blocks ahead: a TMA round trip (~1 us from L2) is longer than one block's work, and
+  // with single buffers every block waited for its tiles (the first version: 437 TFLOP/s whatever else was changed)
+  auto load_k = [&](int blk) {
+    mbar_expect_tx(&bar_k[blk & 1], Cfg::kKvTileBytes);
+    tma_load_3d(sK + (blk & 1) * Cfg::kKvTileBytes, &tm_kv, &bar_k[blk & 1], d + h * kHd, blk * BKV, b);
+  };
+  auto load_v = [&](int blk) {
+    mbar_expect_tx(&bar_v[blk & 1], Cfg::kKvTileBytes);
+    tma_load_3d(sV + (blk & 1) * Cfg::kKvTileBytes, &tm_kv, &bar_v[blk & 1], 2 * d + h * kHd, blk * BKV, b);
+  };
   if (tid == 0) {
-    mbar_expect_tx(bar_q, kTileBytes);
-    tma_load_3d(sQ, &tm_qkv, bar_q, h * kHd, q0, b);
-    mbar_expect_tx(bar_k, kTileBytes);
-    tma_load_3d(sK, &tm_qkv, bar_k, d + h * kHd, 0, b);
-    mbar_expect_tx(bar_v, kTileBytes);
-    tma_load_3d(sV, &tm_qkv, bar_v, 2 * d + h * kHd, 0, b);
+    mbar_expect_tx(bar_q, kQTileBytes);
+    tma_load_3d(sQ, &tm_q, bar_q, h * kHd, q0, b);
+    load_k(0);
+    load_v(0);
+    if (nkv > 1) {
+      load_k(1);
+      load_v(1);
+    }
   }
 
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, BKV, 0, 0);
   constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
   const float c = 0.125f * kLog2e;                              // hd^-0.5 in the exp2 domain
 
-  float m_run = -INFINITY, l_run = 0.0f;
-  float o[kHd];
-#pragma unroll
-  for (int i = 0; i < kHd; ++i) o[i] = 0.0f;
+  // Software pipeline of one CTA (every MMA is issued by thread 0, every barrier below is CTA-wide):
+  //   S(j+1) = Q K(j+1)^T is issued as soon as all four warps hold S(j) in registers, so it runs under softmax(j);
+  //   O accumulates in TMEM across blocks (no per-block read-back); PV(j) is only waited for when block j+1 needs
+  //   the P buffer again.  The running maximum used for exp2 is allowed to lag the true maximum by up to 2^8 (the
+  //   probabilities then reach 256, harmless in bf16 / fp32): O and l are rescaled only when a row's maximum grows by
+  //   more than that, which after the first blocks is rare -- the FlashAttention-4 "conditional rescaling".
+  float m_used = -INFINITY, l_run = 0.0f;
   const int row = tid;  // query row within the tile == TMEM lane
 
-  for (int j = 0; j < nkv; ++j) {
-    const uint32_t ph = j & 1;
-    if (tid == 0) {
-      if (j == 0) mbar_wait(bar_q, 0);
-      mbar_wait(bar_k, ph);
-      tcgen05_fence_after();
-      const uint64_t qd = make_sw128_desc(smem_u32(sQ));
-      const uint64_t kd = make_sw128_desc(smem_u32(sK));
-#pragma unroll
-      for (int k = 0; k < kHd / 16; ++k) umma_f16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-      umma_commit(bar_s);
-    }
-    __syncwarp();
-    mbar_wait(bar_s, ph);
+  if (tid == 0) {
+    mbar_wait(bar_q, 0);
+    mbar_wait(&bar_k[0], 0);
     tcgen05_fence_after();
-    if (tid == 0 && j + 1 < nkv) {  // K tile is free again
-      mbar_expect_tx(bar_k, kTileBytes);
-      tma_load_3d(sK, &tm_qkv, bar_k, d + h * kHd, (j + 1) * kBKV, b);
+    const uint64_t qd = make_sw128_desc(smem_u32(sQ));
+    const uint64_t kd = make_sw128_desc(smem_u32(sK));
+#pragma unroll
+    for (int k = 0; k < kHd / 16; ++k) umma_f16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+
+  for (int j = 0; j < nkv; ++j) {
+    mbar_wait(bar_s, j & 1);
+    tcgen05_fence_after();
+    float sc[BKV];
+    {
+      uint32_t r[BKV];
+#pragma unroll
+      for (int cb = 0; cb < BKV / 32; ++cb) tmem_ld_32x32(tmem_s + cb * 32, reinterpret_cast<uint32_t(&)[32]>(r[cb * 32]));
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < BKV; ++i) sc[i] = __uint_as_float(r[i]);
+    }
+    tcgen05_fence_before();
+    __syncthreads();  // every warp holds its S(j) rows: the S columns and K buffer j & 1 are free
+    if (tid == 0) {
+      tcgen05_fence_after();
+      if (j + 2 < nkv) load_k(j + 2);
+      if (j + 1 < nkv) {
+        mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        tcgen05_fence_after();
+        const uint64_t qd = make_sw128_desc(smem_u32(sQ));
+        const uint64_t kd = make_sw128_desc(smem_u32(sK + ((j + 1) & 1) * Cfg::kKvTileBytes));
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k) umma_f16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+        umma_commit(bar_s);
+      }
     }
     __syncwarp();
 
-    const int kv_valid = min(kBKV, T - j * kBKV);
-    // the whole 128-wide score row of this thread in registers: one pass over TMEM
-    float sc[128];
-    {
-      uint32_t r[32];
+    const int kv_valid = min(BKV, T - j * BKV);
+    if (kv_valid < BKV) {  // only the last key block is ragged (block-uniform branch)
 #pragma unroll
-      for (int cb = 0; cb < 4; ++cb) {
-        tmem_ld_32x32(tmem_s + cb * 32, r);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sc[cb * 32 + i] = __uint_as_float(r[i]);
-      }
-    }
-    if (kv_valid < kBKV) {  // only the last key block is ragged (block-uniform branch)
-#pragma unroll
-      for (int i = 0; i < 128; ++i)
+      for (int i = 0; i < BKV; ++i)
         if (i >= kv_valid) sc[i] = -INFINITY;
     }
-    float mx = sc[0];
+    float mx8[8];
 #pragma unroll
-    for (int i = 1; i < 128; ++i) mx = fmaxf(mx, sc[i]);
-    const float m_new = fmaxf(m_run, mx * c);
-    const float alpha = fast_exp2(m_run - m_new);
-    m_run = m_new;
+    for (int i = 0; i < 8; ++i) mx8[i] = sc[i];
+#pragma unroll
+    for (int i = 8; i < BKV; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], sc[i]);
+    const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+    const float m_cand = fmaxf(m_used, mx * c);
+
+    if (j > 0) {  // PV(j-1) done: P buffer and V buffer (j-1) & 1 are free, O is consistent
+      mbar_wait(bar_o, (j - 1) & 1);
+      tcgen05_fence_after();
+      if (tid == 0 && j + 1 < nkv) load_v(j + 1);
+      __syncwarp();
+      if (__any_sync(0xffffffffu, m_cand > m_used + 8.0f)) {  // warp-uniform: tcgen05.ld / st are warp-collective
+        const float alpha = fast_exp2(m_used - m_cand);     // 1 for the rows of this warp whose maximum did not move
+        m_used = m_cand;
+        l_run *= alpha;
+        uint32_t r[kHd];
+        tmem_ld_32x32(tmem_o, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+        tmem_ld_32x32(tmem_o + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < kHd; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+        tmem_st_32x32(tmem_o, reinterpret_cast<const uint32_t(&)[32]>(r[0]));
+        tmem_st_32x32(tmem_o + 32, reinterpret_cast<const uint32_t(&)[32]>(r[32]));
+        tmem_wait_st();
+      }
+    } else {
+      m_used = m_cand;
+    }
+
     // probabilities -> swizzled bf16 A operand (exp2(-inf) = 0 for the masked tail)
-    float psum = 0.0f;
+    float ps4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int cb = 0; cb < BKV / 32; ++cb) {
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float p0 = fast_exp2(fmaf(sc[cb * 32 + 2 * i], c, -m_new));
-        const float p1 = fast_exp2(fmaf(sc[cb * 32 + 2 * i + 1], c, -m_new));
-        psum += p0 + p1;
+        const float p0 = fast_exp2(fmaf(sc[cb * 32 + 2 * i], c, -m_used));
+        const float p1 = fast_exp2(fmaf(sc[cb * 32 + 2 * i + 1], c, -m_used));
+        ps4[i & 3] += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
       }
       // columns cb*32 .. +31 -> sub-tile cb/2, 16-byte pieces (cb%2)*4 .. +3, XOR-swizzled with row%8
-      unsigned char* base = sP + (cb >> 1) * kTileBytes + row * 128;
+      unsigned char* base = sP + (cb >> 1) * kQTileBytes + row * 128;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int piece = ((cb & 1) * 4 + q) ^ (row & 7);
         *reinterpret_cast<uint4*>(base + piece * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
     }
-    l_run = l_run * alpha + psum;
+    l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
     fence_proxy_async_smem();
     tcgen05_fence_before();
-    __syncthreads();
+    __syncthreads();  // P(j) (and a rescaled O) are in place
     if (tid == 0) {
       tcgen05_fence_after();
-      mbar_wait(bar_v, ph);
+      mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll
-      for (int k = 0; k < kBKV / 16; ++k) {
-        const uint64_t pd = make_sw128_desc(smem_u32(sP + (k >> 2) * kTileBytes)) + 2 * (k & 3);
-        const uint64_t vd = make_sw128_desc_lbo(smem_u32(sV + k * 2048), kBKV * 128);
-        umma_f16(tmem_base + 128, pd, vd, idesc_o, k != 0);
+      for (int k = 0; k < BKV / 16; ++k) {
+        const uint64_t pd = make_sw128_desc(smem_u32(sP + (k >> 2) * kQTileBytes)) + 2 * (k & 3);
+        const uint64_t vd = make_sw128_desc_lbo(smem_u32(sV + (j & 1) * Cfg::kKvTileBytes + k * 2048), BKV * 128);
+        umma_f16(tmem_base + BKV, pd, vd, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
       }
       umma_commit(bar_o);
     }
     __syncwarp();
-    mbar_wait(bar_o, ph);
-    tcgen05_fence_after();
-    if (tid == 0 && j + 1 < nkv) {  // V tile (and P) are free again
-      mbar_expect_tx(bar_v, kTileBytes);
-      tma_load_3d(sV, &tm_qkv, bar_v, 2 * d + h * kHd, (j + 1) * kBKV, b);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_o + cb * 32, r);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[cb * 32 + i] = fmaf(o[cb * 32 + i], alpha, __uint_as_float(r[i]));
-    }
-    tcgen05_fence_before();
   }
 
-  if (q0 + row < T) {
-    const float inv = 1.0f / l_run;
-    uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * T + q0 + row) * d + h * kHd);
+  mbar_wait(bar_o, (nkv - 1) & 1);
+  tcgen05_fence_after();
+  {  // (rows past T exist only in the last query tile; their lanes still take part in the collective TMEM load)
+    uint32_t r[kHd];
+    tmem_ld_32x32(tmem_o, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+    tmem_ld_32x32(tmem_o + 32, reinterpret_cast<uint32_t(&)[32]>(r[32]));
+    tmem_wait_ld();
+    if (q0 + row < T) {
+      const float inv = 1.0f / l_run;
+      uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * T + q0 + row) * d + h * kHd);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      dst[i] = make_uint4(pack_bf16x2(o[8 * i] * inv, o[8 * i + 1] * inv), pack_bf16x2(o[8 * i + 2] * inv, o[8 * i + 3] * inv),
-                          pack_bf16x2(o[8 * i + 4] * inv, o[8 * i + 5] * inv), pack_bf16x2(o[8 * i + 6] * inv, o[8 * i + 7] * inv));
+      for (int i = 0; i < 8; ++i) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * i + e]) * inv;
+        dst[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+// B200W_ENC_BKV=128 selects the first (wide-block) form for A/B runs
+static int enc_bkv() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200W_ENC_BKV");
+    v = (e != nullptr && atoi(e) == 128) ? 128 : 64;
+  }
+  return v;
 }
 
 int init_attention() {
   static bool done = false;
   if (done) return kOk;
-  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmem));
+  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, EncCfg<64>::kSmem));
+  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, EncCfg<128>::kSmem));
   done = true;
   return kOk;
 }
@@ -235,15 +309,21 @@ int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n
                              cudaStream_t stream) {
   B200W_CHECK_ARG(n_batch > 0 && n_batch <= 65535 && T > 0 && n_head > 0, "encoder_attention: bad sizes");
   const int d = n_head * kHd;
-  CUtensorMap tm;
+  const int bkv = enc_bkv();
+  CUtensorMap tq, tkv;
   uint64_t dims[3] = {(uint64_t)(3 * d), (uint64_t)T, (uint64_t)n_batch};
   uint64_t strides[2] = {(uint64_t)(3 * d) * 2, (uint64_t)T * 3 * d * 2};
-  uint32_t box[3] = {kHd, 128, 1};
-  B200W_TRY(encode_tmap_bf16(&tm, qkv, 3, dims, strides, box));
+  uint32_t box_q[3] = {kHd, kBQ, 1};
+  uint32_t box_kv[3] = {kHd, (uint32_t)bkv, 1};
+  B200W_TRY(encode_tmap_bf16(&tq, qkv, 3, dims, strides, box_q));
+  B200W_TRY(encode_tmap_bf16(&tkv, qkv, 3, dims, strides, box_kv));
   B200W_TRY(init_attention());
   dim3 grid(ceil_div(T, kBQ), n_head, n_batch);
   ProfScope prof_("encoder_attention", stream);
-  B200W_CUDA_OK(launch_k(encoder_attention_kernel, grid, dim3(kEncThreads), kEncSmem, stream, tm, T, d, out));
+  if (bkv == 64)
+    B200W_CUDA_OK(launch_k(encoder_attention_kernel<64>, grid, dim3(kEncThreads), EncCfg<64>::kSmem, stream, tq, tkv, T, d, out));
+  else
+    B200W_CUDA_OK(launch_k(encoder_attention_kernel<128>, grid, dim3(kEncThreads), EncCfg<128>::kSmem, stream, tq, tkv, T, d, out));
   count_launch();
   return kOk;
 }
