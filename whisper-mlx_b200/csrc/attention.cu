@@ -49,20 +49,26 @@ constexpr int kEncThreads = 128;
 constexpr int kBQ = 128;
 constexpr int kQTileBytes = kBQ * kHd * 2;  // 16 KB: 128 rows x 128 B
 
-template <int BKV>
+// PT: the probabilities go back to tensor memory (tcgen05.st, over the S columns they were computed from) and P V reads
+// its A operand from there (the TS form of tcgen05.mma): no P tile in shared memory, so neither its 16-32 KB store nor
+// its read per block -- the SS form spends more shared-memory cycles than tensor cycles (A = 4 KB per 128xNx16 MMA).
+#ifndef B200W_ENC_CTAS
+#define B200W_ENC_CTAS 3
+#endif
+template <int BKV, bool PT>
 struct EncCfg {
-  static constexpr int kKvTileBytes = BKV * kHd * 2;   // K or V tile: BKV rows x 128 B
-  static constexpr int kPTileBytes = kBQ * BKV * 2;    // P: BKV / 64 K-major sub-tiles of 128 rows x 128 B
+  static constexpr int kKvTileBytes = BKV * kHd * 2;          // K or V tile: BKV rows x 128 B
+  static constexpr int kPTileBytes = PT ? 0 : kBQ * BKV * 2;  // P: BKV / 64 K-major sub-tiles of 128 rows x 128 B
   static constexpr int kSmem = kQTileBytes + 4 * kKvTileBytes + kPTileBytes + 1024 + 128;  // K and V double-buffered
-  static constexpr int kTmemCols = (BKV + kHd <= 128) ? 128 : 256;  // S (BKV) + O (64), power of two
-  static constexpr int kCtasPerSm = (BKV == 64) ? 3 : 2;  // shared memory: 3 x 65 KB / 2 x 113 KB
+  static constexpr int kTmemCols = (BKV + kHd <= 128) ? 128 : 256;  // S (BKV; P over its first half) + O (64)
+  static constexpr int kCtasPerSm = (BKV == 64) ? (PT ? B200W_ENC_CTAS : 3) : 2;
 };
 
-template <int BKV>
-__global__ void __launch_bounds__(kEncThreads, EncCfg<BKV>::kCtasPerSm)
+template <int BKV, bool PT>
+__global__ void __launch_bounds__(kEncThreads, EncCfg<BKV, PT>::kCtasPerSm)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, int T, int d,
                          __nv_bfloat16* __restrict__ out) {
-  using Cfg = EncCfg<BKV>;
+  using Cfg = EncCfg<BKV, PT>;
   extern __shared__ unsigned char att_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(att_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -166,11 +172,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 #pragma unroll
       for (int i = 0; i < BKV; ++i) sc[i] = __uint_as_float(r[i]);
     }
-    tcgen05_fence_before();
-    __syncthreads();  // every warp holds its S(j) rows: the S columns and K buffer j & 1 are free
-    if (tid == 0) {
-      tcgen05_fence_after();
-      if (j + 2 < nkv) load_k(j + 2);
+    auto issue_next_s = [&]() {  // thread 0 only
       if (j + 1 < nkv) {
         mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
         tcgen05_fence_after();
@@ -180,6 +182,17 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
         for (int k = 0; k < kHd / 16; ++k) umma_f16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
         umma_commit(bar_s);
       }
+    };
+    if constexpr (!PT) {
+      tcgen05_fence_before();
+      __syncthreads();  // every warp holds its S(j) rows: the S columns and K buffer j & 1 are free
+      if (tid == 0) {
+        tcgen05_fence_after();
+        if (j + 2 < nkv) load_k(j + 2);
+        issue_next_s();
+      }
+    } else {
+      if (tid == 0 && j + 2 < nkv) load_k(j + 2);  // S(j) is complete: K buffer j & 1 is free
     }
     __syncwarp();
 
@@ -222,26 +235,41 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 
     // probabilities -> swizzled bf16 A operand (exp2(-inf) = 0 for the masked tail)
     float ps4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if constexpr (PT) {
+      // bf16 pairs (keys 2c, 2c + 1) -> TMEM column c of this thread's lane, over the S columns it has just read
+      uint32_t pk[BKV / 2];
 #pragma unroll
-    for (int cb = 0; cb < BKV / 32; ++cb) {
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float p0 = fast_exp2(fmaf(sc[cb * 32 + 2 * i], c, -m_used));
-        const float p1 = fast_exp2(fmaf(sc[cb * 32 + 2 * i + 1], c, -m_used));
+      for (int i = 0; i < BKV / 2; ++i) {
+        const float p0 = fast_exp2(fmaf(sc[2 * i], c, -m_used));
+        const float p1 = fast_exp2(fmaf(sc[2 * i + 1], c, -m_used));
         ps4[i & 3] += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
       }
-      // columns cb*32 .. +31 -> sub-tile cb/2, 16-byte pieces (cb%2)*4 .. +3, XOR-swizzled with row%8
-      unsigned char* base = sP + (cb >> 1) * kQTileBytes + row * 128;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int piece = ((cb & 1) * 4 + q) ^ (row & 7);
-        *reinterpret_cast<uint4*>(base + piece * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int cb = 0; cb < BKV / 64; ++cb) tmem_st_32x32(tmem_s + cb * 32, reinterpret_cast<const uint32_t(&)[32]>(pk[cb * 32]));
+      tmem_wait_st();
+    } else {
+#pragma unroll
+      for (int cb = 0; cb < BKV / 32; ++cb) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = fast_exp2(fmaf(sc[cb * 32 + 2 * i], c, -m_used));
+          const float p1 = fast_exp2(fmaf(sc[cb * 32 + 2 * i + 1], c, -m_used));
+          ps4[i & 3] += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        // columns cb*32 .. +31 -> sub-tile cb/2, 16-byte pieces (cb%2)*4 .. +3, XOR-swizzled with row%8
+        unsigned char* base = sP + (cb >> 1) * kQTileBytes + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int piece = ((cb & 1) * 4 + q) ^ (row & 7);
+          *reinterpret_cast<uint4*>(base + piece * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
       }
+      fence_proxy_async_smem();
     }
     l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-    fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();  // P(j) (and a rescaled O) are in place
     if (tid == 0) {
@@ -250,11 +278,17 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
       tcgen05_fence_after();
 #pragma unroll
       for (int k = 0; k < BKV / 16; ++k) {
-        const uint64_t pd = make_sw128_desc(smem_u32(sP + (k >> 2) * kQTileBytes)) + 2 * (k & 3);
         const uint64_t vd = make_sw128_desc_lbo(smem_u32(sV + (j & 1) * Cfg::kKvTileBytes + k * 2048), BKV * 128);
-        umma_f16(tmem_base + BKV, pd, vd, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+        if constexpr (PT) {
+          umma_f16_ts(tmem_base + BKV, tmem_base + k * 8, vd, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+        } else {
+          const uint64_t pd = make_sw128_desc(smem_u32(sP + (k >> 2) * kQTileBytes)) + 2 * (k & 3);
+          umma_f16(tmem_base + BKV, pd, vd, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+        }
       }
       umma_commit(bar_o);
+      // the tensor pipe runs this thread's MMAs in order: S(j+1) may overwrite the P columns only after P V(j) read them
+      if constexpr (PT) issue_next_s();
     }
     __syncwarp();
   }
@@ -286,7 +320,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   }
 }
 
-// B200W_ENC_BKV=128 selects the first (wide-block) form for A/B runs
+// A/B switches: B200W_ENC_BKV=128 selects the wide-block form, B200W_ENC_PT=0 the form with P in shared memory
 static int enc_bkv() {
   static int v = -1;
   if (v < 0) {
@@ -295,12 +329,22 @@ static int enc_bkv() {
   }
   return v;
 }
+static bool enc_pt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200W_ENC_PT");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 int init_attention() {
   static bool done = false;
   if (done) return kOk;
-  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, EncCfg<64>::kSmem));
-  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, EncCfg<128>::kSmem));
+  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EncCfg<64, false>::kSmem));
+  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EncCfg<128, false>::kSmem));
+  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EncCfg<64, true>::kSmem));
+  B200W_CUDA_OK(cudaFuncSetAttribute(encoder_attention_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EncCfg<128, true>::kSmem));
   done = true;
   return kOk;
 }
@@ -320,10 +364,15 @@ int launch_encoder_attention(const __nv_bfloat16* qkv, int n_batch, int T, int n
   B200W_TRY(init_attention());
   dim3 grid(ceil_div(T, kBQ), n_head, n_batch);
   ProfScope prof_("encoder_attention", stream);
-  if (bkv == 64)
-    B200W_CUDA_OK(launch_k(encoder_attention_kernel<64>, grid, dim3(kEncThreads), EncCfg<64>::kSmem, stream, tq, tkv, T, d, out));
+  const bool pt = enc_pt();
+  if (bkv == 64 && pt)
+    B200W_CUDA_OK(launch_k(encoder_attention_kernel<64, true>, grid, dim3(kEncThreads), EncCfg<64, true>::kSmem, stream, tq, tkv, T, d, out));
+  else if (bkv == 64)
+    B200W_CUDA_OK(launch_k(encoder_attention_kernel<64, false>, grid, dim3(kEncThreads), EncCfg<64, false>::kSmem, stream, tq, tkv, T, d, out));
+  else if (pt)
+    B200W_CUDA_OK(launch_k(encoder_attention_kernel<128, true>, grid, dim3(kEncThreads), EncCfg<128, true>::kSmem, stream, tq, tkv, T, d, out));
   else
-    B200W_CUDA_OK(launch_k(encoder_attention_kernel<128>, grid, dim3(kEncThreads), EncCfg<128>::kSmem, stream, tq, tkv, T, d, out));
+    B200W_CUDA_OK(launch_k(encoder_attention_kernel<128, false>, grid, dim3(kEncThreads), EncCfg<128, false>::kSmem, stream, tq, tkv, T, d, out));
   count_launch();
   return kOk;
 }
