@@ -626,7 +626,8 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   const int kg = lane >> 3;   // which of the warp's 4 concurrent keys
   const int d = n_head * kHd;
   const long long ld = 2ll * d;  // K | V interleaved per row
-  const int h = blockIdx.x, b = blockIdx.y, qi = blockIdx.z;
+  // queries of one (sequence, head) are adjacent CTAs: they stream the same K/V rows and share them through L2
+  const int qi = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   pdl_wait();
   pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   if (finished != nullptr && finished[b]) return;  // no K/V streaming for sequences that have emitted EOT
@@ -766,7 +767,7 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
   B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "cross_attention: bad sizes");
   B200W_CHECK_ARG(n_split > 0 ? (part && bias) : (q != nullptr), "cross_attention: missing query input");
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
-  dim3 grid(n_head, n_seq, n_q);
+  dim3 grid(n_q, n_head, n_seq);
   ProfScope prof_("decoder_cross_attention", stream);
   if (probs_out != nullptr)
     B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel<true>, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head,
