@@ -137,7 +137,7 @@ def kernel_rooflines(model, peaks, n_windows: int):
     bytes_alg = n_windows * T * 2 * d * 2  # K and V rows of every window, bf16, read once
     # DRAM traffic per launch from the ncu --set full capture of this kernel at 120 windows
     # (profiles/r01_ncu_full_summaries.json: 921.93 MB read + 4.60 MB written), scaled to this launch's windows
-    traffic = (921_934_848 + 4_597_504) * n_windows / 120.0 if d == 1280 else None
+    traffic = (921_940_480 + 4_274_944) * n_windows / 120.0 if d == 1280 else None  # profiles/r01_ncu_full_summaries_v2.json
     out["cross_attention_decode"] = {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                      "frac": bytes_alg / t / 1e9 / peaks["hbm_gbs"], "traffic": traffic, "launch_ms": t * 1e3,
                                      "algorithmic_bytes_per_launch": bytes_alg}

@@ -856,4 +856,16 @@ int b200w_dtw(const float* matrix, long long ld, int N, int M, float* cost, sign
   return launch_dtw(matrix, ld, N, M, cost, trace, text_idx, time_idx, path_len, (cudaStream_t)stream);
 }
 
+// development probe (tools/probe_chain.py; not part of the public header): a chain of n_phases empty phases, i.e.
+// n_phases - 1 grid barriers and nothing else
+int b200w_debug_chain_barriers(int n_phases, unsigned int* counter, float* x, void* h, const float* gamma, void* stream) {
+  ChainMaps maps{};
+  ChainParams cp{};
+  cp.rows = 0;
+  cp.counter = counter;
+  for (int i = 0; i < n_phases; ++i)
+    B200W_TRY(chain_add_ln(&cp, x, nullptr, 0, 0, nullptr, gamma, gamma, 128, (__nv_bfloat16*)h));
+  return launch_chain(maps, cp, (cudaStream_t)stream);
+}
+
 }  // extern "C"
