@@ -41,16 +41,17 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned int* counter, unsign
   fence_proxy_async_global();  // this thread's generic-proxy global writes are ordered before later TMA reads
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    // release: the CTA's writes (ordered before this thread by the bar.sync above) are visible device-wide before the
+    // arrival; acquire on the poll orders everything after it.  Explicit __threadfence() on both sides measured
+    // 1.84 us per barrier (tools/probe_chain.py); the two fences are implied by .release / .acquire.
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");  // no return value to wait for
     unsigned int spins = 0;
     while (ld_acquire_gpu(counter) < target) {
       if (++spins > (1u << 26)) __trap();  // a lost CTA must not hang the GPU
     }
-    __threadfence();
   }
   __syncthreads();
-  fence_proxy_async_global();
+  fence_proxy_async_global();  // (measured free: 1.53 us per barrier with or without it)
 }
 
 __global__ void __launch_bounds__(kChThreads, 1)
