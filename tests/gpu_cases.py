@@ -99,7 +99,8 @@ def case_logmel_shapes():
     from whisper_mlx_b200.audio import log_mel_spectrogram
 
     out = {}
-    for n, pad in ((480000, 480000), (16000 * 7 + 123, 0), (4001, 0), (1000, 480000), (160 * 33, 160 * 5), (401, 0)):
+    for n, pad in ((480000, 480000), (16000 * 7 + 123, 0), (4001, 0), (1000, 480000), (160 * 33, 160 * 5), (401, 0),
+                   (150, 480000), (1, 1600)):  # shorter than the reflect pad: legal once zero-extended
         e, _ = _logmel_err(synth.white_noise(n, n), 80, pad)
         out[f"n{n}_p{pad}"] = e
         assert e <= LOGMEL_TOL, (n, pad, e)

@@ -209,3 +209,20 @@ def test_finished_sequences_are_skipped_without_touching_the_others(micro_dir):
     assert torch.equal(full[0], part[0]) and torch.equal(full[2], part[2])
     assert bool((part[1, n0:] == eot).all()) and bool((part[3, n0:] == eot).all())
     assert not bool((full[1, n0:] == eot).all())
+
+
+def test_empty_and_very_short_audio(micro_dir):
+    """Zero samples and a few milliseconds of audio transcribe without error (the 30 s zero padding makes the signal
+    long enough for the reflect pad); log-mel of a too-short unpadded signal is rejected with a clear message."""
+    from whisper_mlx_b200 import transcribe
+    from whisper_mlx_b200.audio import log_mel_spectrogram
+    from whisper_mlx_b200.load_models import load_model
+
+    m = load_model(micro_dir)
+    for x in (np.zeros(0, dtype=np.float32), synth.white_noise(100, 0), np.zeros(0, dtype=np.int16)):
+        r = transcribe(x, model=m, language="en", temperature=0.0, sample_len=8)
+        assert set(r) == {"text", "segments", "language"} and isinstance(r["segments"], list)
+    mel = log_mel_spectrogram(np.zeros(0, dtype=np.float32), n_mels=80, padding=480000)
+    assert mel.shape == (3000, 80) and bool(torch.isfinite(mel).all())
+    with pytest.raises(ValueError, match="reflect pad"):
+        log_mel_spectrogram(synth.white_noise(150, 0), n_mels=80)

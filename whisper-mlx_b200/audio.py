@@ -193,6 +193,10 @@ def log_mel_unclamped(audio: torch.Tensor, n_mels: int = 80, padding: int = 0) -
     _lib.require_cuda(x, "audio")
     n_audio, n_valid = x.shape
     n_total = n_valid + padding
+    if n_total <= N_FFT // 2:
+        raise ValueError(f"audio of {n_valid} samples (+{padding} padding) is shorter than the {N_FFT // 2}-sample reflect pad")
+    if n_valid == 0:  # empty input with padding: all-zero signal; the kernel still wants a valid pointer
+        x = torch.zeros((n_audio, 1), dtype=x.dtype, device=x.device)
     n_frames = n_total // HOP_LENGTH
     tb = _get_tables(x.device, n_mels)
     out = torch.empty((n_audio, n_frames, n_mels), dtype=torch.float32, device=x.device)

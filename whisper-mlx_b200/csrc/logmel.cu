@@ -306,7 +306,9 @@ template <typename PcmT>
 static int launch_logmel_t(const PcmT* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
                            int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
                            cudaStream_t stream) {
-  B200W_CHECK_ARG(n_audio > 0 && n_valid > kNfft / 2 && n_total >= n_valid, "logmel: bad sizes");
+  // the reflect pad works on the zero-extended signal (UPSTREAM pads first): only its total length must exceed the pad
+  B200W_CHECK_ARG(n_audio > 0 && n_valid >= 0 && n_total >= n_valid && n_total > kNfft / 2,
+                  "logmel: the (zero-extended) signal must be longer than the 200-sample reflect pad");
   B200W_CHECK_ARG(n_mels == 80 || n_mels == 128, "logmel: n_mels must be 80 or 128, got %d", n_mels);
   const long long n_frames_ll = n_total / kHop;
   B200W_CHECK_ARG(n_frames_ll > 0 && n_frames_ll < (1ll << 31) / 128, "logmel: frame count out of range");
