@@ -2,12 +2,12 @@
 // reached from /root/reference/run:3-6).  Head dim is 64 for every Whisper size; the
 // reference scales q and k by hd^-0.25 each, here the product hd^-0.5 is folded into the fp32 scores.
 //
-// K6 encoder MHA (non-causal, S = 1500): flash-style on tcgen05.  One CTA = 128 queries of one head.
-//    Q/K/V tiles arrive by TMA (128-byte swizzle) straight out of the fused QKV activation;
-//    S = Q K^T (128x128x64) and O_blk = P V (128x64x128, V consumed MN-major) run on the tensor cores
-//    with accumulators in TMEM; each of the 128 threads owns one query row (one TMEM lane): softmax
-//    needs no shuffles, P goes back to shared memory as the swizzled bf16 A operand, and the running
-//    output is rescaled in registers.  Two CTAs per SM overlap one CTA's exp work with the other's MMAs.
+// K6 encoder MHA (non-causal, S = 1500): flash-style on tcgen05.  One CTA = 128 queries of one head, key blocks
+//    of 64.  Q/K/V tiles arrive by TMA (128-byte swizzle) straight out of the fused QKV activation, K/V two blocks
+//    ahead; S = Q K^T runs SS (both operands in shared memory), each of the 128 threads owns one query row (one
+//    TMEM lane) so softmax needs no shuffles, P goes back to tensor memory and P V runs TS (A operand from TMEM,
+//    V consumed MN-major); the output accumulates in TMEM and is rescaled only when a row maximum moves by > 2^8.
+//    Three CTAs per SM overlap one CTA's exp work with the others' MMAs and TMEM round trips.
 // K7 decoder self-attention over the paged KV cache (q-len 1, or a short prompt), CUDA cores.
 // K8 decoder cross-attention (S = 1500), the HBM-bound hot spot of decoding: 16-byte coalesced loads,
 //    8 lanes per key row, each K/V byte read exactly once per step.
