@@ -38,7 +38,8 @@ if __name__ == "__main__":
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 40
     res = {}
     for flag in ("0", "1", "1"):
-        env = dict(os.environ, B200W_CHAIN=flag)
+        # the unfused path plans its K splits like the (multicast) chain does, so that the sums run in the same order
+        env = dict(os.environ, B200W_CHAIN=flag, B200W_SPLIT_PLAN="mc")
         out = subprocess.run([sys.executable, __file__, "child", model, str(windows), str(steps)], env=env, capture_output=True,
                              text=True, timeout=600)
         if out.returncode != 0:

@@ -178,14 +178,30 @@ static int gemm(const void* A, long long lda, int M, const void* W, int N, int K
 // Split-K plan for a single-row-tile (decode) GEMM: enough K slices that ~all SMs stream weights, each slice
 // at least two K blocks.  Per-SM TMA ingest (~85 GB/s measured) times the per-CTA bytes is what bounds these
 // launches, so the work is spread over as many CTAs as fit in one wave.
-static int plan_split_k(int N, int K, int bn) {
-  const int tiles = ceil_div(N, bn), num_kb = ceil_div(K, 64);
-  int s = device_sm_count() / tiles;
+// Split-K plan of a <= 128-row GEMM: `workers` CTAs (or clusters of `group` CTAs in the multicast chain, each cluster
+// taking `group` neighbouring column tiles of one K range) share N / bn column tiles x s K slices.
+static int plan_split_k(int N, int K, int bn, int group = 1, int workers = 0) {
+  const int tiles = ceil_div(ceil_div(N, bn), group), num_kb = ceil_div(K, 64);
+  if (workers <= 0) workers = device_sm_count();
+  int s = workers / tiles;
   if (s > 8) s = 8;
   if (s > num_kb / 2) s = num_kb / 2;
   if (s < 1) s = 1;
   const int kb_per = ceil_div(num_kb, s);
   return ceil_div(num_kb, kb_per);
+}
+
+// The chain's cluster-multicast form walks its work list with mc_grid / 4 clusters: plan the K splits for that many
+// workers when it will be used (B200W_SPLIT_PLAN=mc forces the same plan on the unfused path, for bit-exact A/B runs).
+static bool use_mc_plan(int rows, int d) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("B200W_SPLIT_PLAN");
+    forced = (e != nullptr && strcmp(e, "mc") == 0) ? 1 : 0;
+  }
+  const int g = chain_mc_grid();
+  const bool shapes_ok = g >= rows && g > 0 && d % 256 == 0;  // every GEMM of the layer has a multiple of 4 column tiles
+  return shapes_ok && (forced == 1 || chain_enabled());
 }
 
 // part[s] (M, ldp) f32 = A(:, K-slice s) W(:, K-slice s)^T for s < split (the consumer kernel sums the slabs)
@@ -635,7 +651,10 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
     // K11: the small-M phases between the attention kernels run as three chains per layer
     //   [LN -> QKV]  SA  [out -> LN -> q]  CA  [out -> LN -> MLP1 -> MLP2 -> LN -> next layer's QKV]
     const long long s3 = 128ll * 3 * d, s1 = 128ll * d;
-    const int sp_qkv = plan_split_k(3 * d, d, 64), sp_d = plan_split_k(d, d, 64), sp_mlp2 = plan_split_k(d, 4 * d, 64);
+    const bool mcp = use_mc_plan(rows, d);
+    const int grp = mcp ? 4 : 1, wk = mcp ? chain_mc_grid() / 4 : 0;
+    const int sp_qkv = plan_split_k(3 * d, d, 64, grp, wk), sp_d = plan_split_k(d, d, 64, grp, wk),
+              sp_mlp2 = plan_split_k(d, 4 * d, 64, grp, wk);
     B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, kChainCounters * sizeof(unsigned int), stream));
     int n_chain = 0;
     __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(bf.h);
@@ -690,7 +709,10 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   } else if (small) {
     const int bn = 64;
     const long long s3 = 128ll * 3 * d, s1 = 128ll * d;
-    const int sp_qkv = plan_split_k(3 * d, d, bn), sp_d = plan_split_k(d, d, bn), sp_mlp2 = plan_split_k(d, 4 * d, bn);
+    const bool mcp = use_mc_plan(rows, d);
+    const int grp = mcp ? 4 : 1, wk = mcp ? chain_mc_grid() / 4 : 0;
+    const int sp_qkv = plan_split_k(3 * d, d, bn, grp, wk), sp_d = plan_split_k(d, d, bn, grp, wk),
+              sp_mlp2 = plan_split_k(d, 4 * d, bn, grp, wk);
     int pend = 0;  // split count of the residual GEMM whose partials (+ bias) the next LayerNorm folds into x
     const float* pend_bias = nullptr;
     for (int l = 0; l < dm.n_text_layer; ++l) {
@@ -855,6 +877,8 @@ int b200w_dtw(const float* matrix, long long ld, int N, int M, float* cost, sign
   B200W_CHECK_ARG(matrix && cost && trace && text_idx && time_idx && path_len, "dtw: null pointer");
   return launch_dtw(matrix, ld, N, M, cost, trace, text_idx, time_idx, path_len, (cudaStream_t)stream);
 }
+
+int b200w_debug_chain_mc_grid() { return chain_mc_grid(); }
 
 // development probe (tools/probe_chain.py; not part of the public header): a chain of n_phases empty phases, i.e.
 // n_phases - 1 grid barriers and nothing else

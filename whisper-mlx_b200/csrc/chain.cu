@@ -36,6 +36,32 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t chain_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void chain_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load delivered to the same shared-memory offset of every CTA in `mask`, completing on each one's barrier
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], "
+      "[%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once this thread's prior MMAs have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // All CTAs of the (cooperative, co-resident) grid meet here; `target` = CTAs x barriers passed so far.
 __device__ __forceinline__ void chain_grid_barrier(unsigned int* counter, unsigned int target) {
   fence_proxy_async_global();  // this thread's generic-proxy global writes are ordered before later TMA reads
@@ -54,6 +80,13 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned int* counter, unsign
   fence_proxy_async_global();  // (measured free: 1.53 us per barrier with or without it)
 }
 
+// MC: clusters of kChCluster CTAs take the kChCluster neighbouring column tiles of one K range and share the A operand:
+// every CTA loads a quarter of the 128 x 64 A tile and multicasts it to the cluster, so a CTA ingests 4 + 8 KB per K
+// block instead of 16 + 8 KB (the <= 128-row GEMMs are bound by the per-SM operand ingest; the same activations used
+// to be fetched by every CTA).  A stage is released to its four producers by the four MMA issuers (multicast commit).
+constexpr int kChCluster = 4;
+
+template <bool MC>
 __global__ void __launch_bounds__(kChThreads, 1)
 decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   extern __shared__ unsigned char chain_smem_raw[];
@@ -68,15 +101,19 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
   __shared__ float s_red[2][kChThreads / 32];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int crank = MC ? (int)chain_cluster_rank() : 0;
+  constexpr int kGroup = MC ? kChCluster : 1;            // CTAs that walk one work list together
+  const int worker = blockIdx.x / kGroup, n_workers = gridDim.x / kGroup;
+  constexpr uint16_t kMask = (1u << kChCluster) - 1;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.n_gemm; ++i) {
-      tma_prefetch_desc(&maps.a[i]);
+      tma_prefetch_desc(MC ? &maps.a4[i] : &maps.a[i]);
       tma_prefetch_desc(&maps.b[i]);
     }
     for (int i = 0; i < kChStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kGroup);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -90,6 +127,7 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (MC) chain_cluster_sync();  // every CTA's barriers exist before a peer's multicast can signal them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -105,11 +143,11 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
   int pre_cnt = 0, pre_stage0 = 0;
   auto prefetch_w = [&](const ChainPhase& Q) {
     const CUtensorMap* qb = &maps.b[Q.map];
-    const int q_tiles = Q.tiles_n * Q.split_k;
+    const int q_tiles = (Q.tiles_n / kGroup) * Q.split_k;
     pre_stage0 = stage;
     pre_cnt = 0;
-    for (int tile = blockIdx.x; tile < q_tiles && pre_cnt < kChStages; tile += gridDim.x) {
-      const int ks = tile % Q.split_k, nt = tile / Q.split_k;
+    for (int tile = worker; tile < q_tiles && pre_cnt < kChStages; tile += n_workers) {
+      const int ks = tile % Q.split_k, nt = (tile / Q.split_k) * kGroup + crank;
       const int kb_end = min(Q.num_kb, (ks + 1) * Q.kb_per_split);
       for (int kb = ks * Q.kb_per_split; kb < kb_end && pre_cnt < kChStages; ++kb, ++pre_cnt) {
         mbar_wait(&empty_bar[stage], ring_phase ^ 1);
@@ -126,25 +164,32 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
   for (int ph = 0; ph < p.n_phases; ++ph) {
     const ChainPhase& P = p.ph[ph];
     if (P.kind == kChainGemm) {
-      const int num_tiles = P.tiles_n * P.split_k;
-      const CUtensorMap* ta = &maps.a[P.map];
+      const int num_tiles = (P.tiles_n / kGroup) * P.split_k;  // work items of this CTA's group
+      const CUtensorMap* ta = MC ? &maps.a4[P.map] : &maps.a[P.map];
       const CUtensorMap* tb = &maps.b[P.map];
       if (warp == 0) {
         if (lane == 0) {
           int item = 0;
-          for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int ks = tile % P.split_k, nt = tile / P.split_k;
+          auto load_a = [&](int slot, int kb) {  // the whole A tile, or this CTA's quarter of it for the whole cluster
+            unsigned char* sa = smem + slot * kChStageBytes;
+            if constexpr (MC)
+              tma_load_3d_mc(sa + crank * (kChABytes / kChCluster), ta, &full_bar[slot], kb * kChBK, crank * (kChBM / kChCluster), 0,
+                             kMask);
+            else
+              tma_load_3d(sa, ta, &full_bar[slot], kb * kChBK, 0, 0);
+          };
+          for (int tile = worker; tile < num_tiles; tile += n_workers) {
+            const int ks = tile % P.split_k, nt = (tile / P.split_k) * kGroup + crank;
             const int kb_end = min(P.num_kb, (ks + 1) * P.kb_per_split);
             for (int kb = ks * P.kb_per_split; kb < kb_end; ++kb, ++item) {
               if (item < pre_cnt) {  // W tile already in flight (issued before the grid barrier): only A is missing
-                const int slot = (pre_stage0 + item) % kChStages;
-                tma_load_3d(smem + slot * kChStageBytes, ta, &full_bar[slot], kb * kChBK, 0, 0);
+                load_a((pre_stage0 + item) % kChStages, kb);
                 continue;
               }
               mbar_wait(&empty_bar[stage], ring_phase ^ 1);
               unsigned char* sa = smem + stage * kChStageBytes;
               mbar_expect_tx(&full_bar[stage], kChStageBytes);
-              tma_load_3d(sa, ta, &full_bar[stage], kb * kChBK, 0, 0);
+              load_a(stage, kb);
               tma_load_3d(sa + kChABytes, tb, &full_bar[stage], kb * kChBK, nt * kChBN, 0);
               if (++stage == kChStages) {
                 stage = 0;
@@ -159,7 +204,7 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
       } else if (warp == 1) {
         if (lane == 0) {
           constexpr uint32_t idesc = make_idesc_bf16(kChBM, kChBN, 0, 0);
-          for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          for (int tile = worker; tile < num_tiles; tile += n_workers) {
             mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * kChBN;
@@ -174,7 +219,8 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
 #pragma unroll
               for (int k = 0; k < kChBK / 16; ++k)
                 umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb_begin || k != 0) ? 1u : 0u);
-              umma_commit(&empty_bar[stage]);
+              if constexpr (MC) umma_commit_mc(&empty_bar[stage], kMask);  // the slot is refilled by all four producers
+              else umma_commit(&empty_bar[stage]);
               if (++stage == kChStages) {
                 stage = 0;
                 ring_phase ^= 1;
@@ -193,8 +239,8 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         float* stg = reinterpret_cast<float*>(smem + kChStages * kChStageBytes + 256) + e * (32 * 33);
         const int t0 = q * 32;
         const int rows_here = min(32, p.rows - t0);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int ks = tile % P.split_k, nt = tile / P.split_k;
+        for (int tile = worker; tile < num_tiles; tile += n_workers) {
+          const int ks = tile % P.split_k, nt = (tile / P.split_k) * kGroup + crank;
           mbar_wait(&tmem_full_bar[acc], acc_phase);
           tcgen05_fence_after();
           const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kChBN;
@@ -284,21 +330,55 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
 
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (MC) chain_cluster_sync();  // no CTA leaves while a peer may still signal its barriers
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kChTmemCols);
   }
 }
 
+static int g_chain_mc_grid = 0;  // CTAs of the multicast form that can be co-resident (0: unavailable)
+
 int init_chain() {
   static bool done = false;
   if (done) return kOk;
-  B200W_CUDA_OK(cudaFuncSetAttribute(decode_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes));
+  B200W_CUDA_OK(cudaFuncSetAttribute(decode_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes));
+  B200W_CUDA_OK(cudaFuncSetAttribute(decode_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes));
+  // B200W_CHAIN_MC=1 opts into the cluster-multicast form.  Measured on B200 (large-v3, 120 sequences): 7.46 ms per step
+  // against 7.44 ms without it -- only 33 clusters of 4 fit at once (132 of 148 SMs), the four CTAs of a cluster advance
+  // in lockstep, and a phase is dominated by its fixed ~4.5 us, not by operand ingest.  Off by default.
+  const char* e = getenv("B200W_CHAIN_MC");
+  if (e != nullptr && e[0] == '1') {
+    // clusters of 4 must sit inside one GPC: ask how many fit at once, the cooperative grid cannot be larger
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(device_sm_count() / kChCluster * kChCluster);
+    cfg.blockDim = dim3(kChThreads);
+    cfg.dynamicSmemBytes = kChSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kChCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, decode_chain_kernel<true>, &cfg) == cudaSuccess && n_clusters > 0) {
+      const int cap = device_sm_count() / kChCluster;
+      g_chain_mc_grid = (n_clusters < cap ? n_clusters : cap) * kChCluster;
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
   done = true;
   return kOk;
 }
 
 // ---------------------------------------------------------------------------------------------- host
+int chain_mc_grid() {
+  if (init_chain() != kOk) return -1;
+  return g_chain_mc_grid;
+}
+
 int chain_add_gemm(ChainMaps* maps, ChainParams* p, const void* A, long long lda, const void* W, int N, int K, int split_k,
                    void* out, long long ldc, long long split_stride, const float* bias, bool gelu) {
   B200W_CHECK_ARG(p->n_phases < kChainMaxPhases && p->n_gemm < kChainMaxGemm, "chain: too many phases");
@@ -309,6 +389,12 @@ int chain_add_gemm(ChainMaps* maps, ChainParams* p, const void* A, long long lda
   P.kind = kChainGemm;
   P.map = p->n_gemm++;
   B200W_TRY(make_tmap_a(&maps->a[P.map], A, 1, p->rows, K, lda, (long long)p->rows * lda));
+  {  // the same operand in quarter-tile boxes (32 rows) for the multicast form
+    uint64_t dims[3] = {(uint64_t)K, (uint64_t)p->rows, 1};
+    uint64_t strides[2] = {(uint64_t)lda * 2, (uint64_t)p->rows * lda * 2};
+    uint32_t box[3] = {kChBK, kChBM / kChCluster, 1};
+    B200W_TRY(encode_tmap_bf16(&maps->a4[P.map], A, 3, dims, strides, box));
+  }
   B200W_TRY(make_tmap_w(&maps->b[P.map], W, N, K, kChBN));
   P.tiles_n = N / kChBN;
   P.num_kb = K / kChBK;
@@ -347,18 +433,29 @@ int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t strea
   B200W_CHECK_ARG(p.n_phases > 0 && p.counter != nullptr, "chain: empty chain or no barrier counter");
   B200W_CHECK_ARG(p.rows <= device_sm_count(), "chain: one LayerNorm row per CTA needs rows <= SM count");
   B200W_TRY(init_chain());
+  // the multicast form needs every GEMM phase to have a multiple of 4 column tiles and a grid that holds the rows
+  bool mc = g_chain_mc_grid >= p.rows && g_chain_mc_grid > 0;
+  for (int i = 0; i < p.n_phases; ++i)
+    if (p.ph[i].kind == kChainGemm && p.ph[i].tiles_n % kChCluster != 0) mc = false;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(device_sm_count());
+  cfg.gridDim = dim3(mc ? g_chain_mc_grid : device_sm_count());
   cfg.blockDim = dim3(kChThreads);
   cfg.dynamicSmemBytes = kChSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barriers cannot deadlock
   attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = kChCluster;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = mc ? 2 : 1;
   ProfScope prof_("dec_chain", stream);
-  B200W_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_chain_kernel, maps, p));
+  if (mc)
+    B200W_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_chain_kernel<true>, maps, p));
+  else
+    B200W_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_chain_kernel<false>, maps, p));
   count_launch();
   return kOk;
 }
