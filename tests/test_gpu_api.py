@@ -226,3 +226,16 @@ def test_empty_and_very_short_audio(micro_dir):
     assert mel.shape == (3000, 80) and bool(torch.isfinite(mel).all())
     with pytest.raises(ValueError, match="reflect pad"):
         log_mel_spectrogram(synth.white_noise(150, 0), n_mels=80)
+
+
+def test_decode_chain_is_bit_identical_to_separate_launches():
+    """K11 (the decode chain) runs the same arithmetic in the same order as the per-phase launches it replaces:
+    tokens and logits of a 64-sequence whisper-small decode must match bit for bit (tools/ab_chain.py runs the
+    B200W_CHAIN=0 / =1 halves in separate processes)."""
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(repo, "tools", "ab_chain.py"), "small", "64", "12"], capture_output=True,
+                         text=True, timeout=600, cwd=repo)
+    assert out.returncode == 0 and "IDENTICAL" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
