@@ -171,6 +171,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     float* stage = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256) + e * (32 * 33);
     int acc = 0;
     uint32_t acc_phase = 0;
+    // the 16-byte f32 epilogue needs aligned rows (whole 32-column chunks are always stored: ldc >= n_store rounded up)
+    const bool vec_f32 = p.out_f32 && (p.ldc & 3) == 0 && (p.split_stride & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+                         (p.resid == nullptr || ((p.resid_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.resid) & 15) == 0)) &&
+                         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mt, nt, ks;
       decode_tile(tile, mt, nt, ks);
@@ -185,6 +190,58 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int col = n0 + c * 32;
         if (col >= p.n_store) break;  // warp-uniform
         const int rows_here = min(32, p.rows_per_batch - t0);  // rows of this warp that exist (may be <= 0)
+        if (vec_f32) {
+          // f32 output, 16-byte form: a lane owns four consecutive columns (sub) of rows rq, rq + 4, ... so that one
+          // instruction moves four full 128-byte row segments -- a quarter of the load / store instructions of the
+          // scalar form below, which kept the out-projection (K = d) waiting on its own epilogue.  Reading the padded
+          // transpose tile as 4 scalars per lane is conflict-free (row stride 33: the four rows of an instruction start
+          // one bank apart, the eight column groups four banks apart).
+          const int sub = lane & 7, rq = lane >> 3;
+          float4 rs4[8];
+          if (p.resid != nullptr) {
+            const long long lrow0 = (long long)b * p.rows_per_batch + t0;
+            const float* rp = p.resid + col + 4 * sub;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + rq;
+              long long ridx = lrow0 + rr;
+              if (p.resid_mod > 0) ridx %= p.resid_mod;
+              rs4[i] = (rr < rows_here) ? *reinterpret_cast<const float4*>(rp + ridx * p.resid_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rs4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          uint32_t r[32];
+          tmem_ld_32x32(t_base + c * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * sub));
+          float* op = reinterpret_cast<float*>(p.out) + ks * p.split_stride + ((long long)b * p.out_batch_rows + t0) * p.ldc + col +
+                      4 * sub;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + rq;
+            const float* sp = stage + rr * 33 + 4 * sub;
+            float4 v = make_float4(sp[0] + b4.x, sp[1] + b4.y, sp[2] + b4.z, sp[3] + b4.w);
+            if (p.gelu) {
+              v.x = gelu_fast(v.x);
+              v.y = gelu_fast(v.y);
+              v.z = gelu_fast(v.z);
+              v.w = gelu_fast(v.w);
+            }
+            v.x += rs4[i].x;
+            v.y += rs4[i].y;
+            v.z += rs4[i].z;
+            v.w += rs4[i].w;
+            if (rr < rows_here) *reinterpret_cast<float4*>(op + (long long)rr * p.ldc) = v;
+          }
+          __syncwarp();
+          continue;
+        }
         // residual rows first: 32 independent coalesced loads in flight while the accumulator is fetched and transposed
         float rsd[32];
         if (p.out_f32 && p.resid != nullptr) {
