@@ -252,10 +252,15 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
           for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
           __syncwarp();
           if (!P.gelu) {
-            float* op = reinterpret_cast<float*>(P.out) + ks * P.split_stride + (long long)t0 * P.ldc + col + lane;
+            // 16-byte stores: a lane owns four columns of rows rq, rq + 4, ... (conflict-free reads of the padded tile)
+            const int sub = lane & 7, rq = lane >> 3;
+            float* op = reinterpret_cast<float*>(P.out) + ks * P.split_stride + (long long)t0 * P.ldc + col + 4 * sub;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr)
-              if (rr < rows_here) op[(long long)rr * P.ldc] = stg[rr * 33 + lane];
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + rq;
+              const float* sp = stg + rr * 33 + 4 * sub;
+              if (rr < rows_here) *reinterpret_cast<float4*>(op + (long long)rr * P.ldc) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            }
           } else {
             const int l2 = (lane & 15) * 2, hi = lane >> 4;
             const float b0 = __ldg(P.bias + col + l2), b1 = __ldg(P.bias + col + l2 + 1);
@@ -384,6 +389,8 @@ int chain_add_gemm(ChainMaps* maps, ChainParams* p, const void* A, long long lda
   B200W_CHECK_ARG(p->n_phases < kChainMaxPhases && p->n_gemm < kChainMaxGemm, "chain: too many phases");
   B200W_CHECK_ARG(N % kChBN == 0 && K % kChBK == 0 && p->rows > 0 && p->rows <= kChBM, "chain: unsupported GEMM shape");
   B200W_CHECK_ARG(!gelu || (split_k <= 1 && bias != nullptr), "chain: GELU phase cannot be split");
+  B200W_CHECK_ARG(gelu || ((ldc & 3) == 0 && (split_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0),
+                  "chain: partial slabs must be 16-byte aligned");
   ChainPhase& P = p->ph[p->n_phases++];
   P = ChainPhase{};
   P.kind = kChainGemm;

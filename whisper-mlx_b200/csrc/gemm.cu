@@ -176,6 +176,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                          (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
                          (p.resid == nullptr || ((p.resid_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.resid) & 15) == 0)) &&
                          (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+    const bool vec_bf16 = !p.out_f32 && (p.ldc & 7) == 0 && ((p.out_batch_rows * p.ldc) & 7) == 0 &&
+                          (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mt, nt, ks;
       decode_tile(tile, mt, nt, ks);
@@ -273,6 +275,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (p.gelu) v = gelu_fast(v);
             v += rsd[rr];
             if (rr < rows_here) op[(long long)rr * p.ldc] = v;
+          }
+        } else if (vec_bf16) {
+          // bf16 output, 16-byte form: a lane owns eight consecutive columns of rows r8, r8 + 8, ...: one instruction
+          // stores eight full 64-byte row segments (conflict-free reads: bank = r8 + 8 * s4 + j mod 32)
+          const int s4 = lane & 3, r8 = lane >> 2;
+          float bs[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bs[j] = (p.bias != nullptr) ? __ldg(p.bias + col + 8 * s4 + j) : 0.0f;
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.out_batch_rows + t0) * p.ldc + col + 8 * s4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + r8;
+            const float* sp = stage + rr * 33 + 8 * s4;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j] = sp[j] + bs[j];
+              if (p.gelu) v[j] = gelu_fast(v[j]);
+            }
+            if (rr < rows_here)
+              *reinterpret_cast<uint4*>(op + (long long)rr * p.ldc) =
+                  make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           }
         } else {
           // two rows per pass: lanes 0-15 the even row, lanes 16-31 the odd one, two adjacent columns per lane

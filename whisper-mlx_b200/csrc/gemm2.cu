@@ -199,6 +199,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool vec_bf16 = !p.out_f32 && (p.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
       int mt, nt;
       decode_tile(tile, mt, nt);
@@ -235,6 +236,27 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             if (p.gelu) v = gelu_fast(v);
             v += rsd[rr];
             if (rr < rows_here) op[(long long)rr * p.ldc] = v;
+          }
+        } else if (vec_bf16) {
+          // 16-byte stores: a lane owns eight consecutive columns of rows r8, r8 + 8, ... (as in gemm.cu)
+          const int s4 = lane & 3, r8 = lane >> 2;
+          float bs[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bs[j] = (p.bias != nullptr) ? __ldg(p.bias + col + 8 * s4 + j) : 0.0f;
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)t0 * p.ldc + col + 8 * s4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + r8;
+            const float* sp = stage_buf + rr * 33 + 8 * s4;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j] = sp[j] + bs[j];
+              if (p.gelu) v[j] = gelu_fast(v[j]);
+            }
+            if (rr < rows_here)
+              *reinterpret_cast<uint4*>(op + (long long)rr * p.ldc) =
+                  make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           }
         } else {
           const int l2 = (lane & 15) * 2, hi = lane >> 4;
