@@ -239,3 +239,18 @@ def test_decode_chain_is_bit_identical_to_separate_launches():
     out = subprocess.run([sys.executable, os.path.join(repo, "tools", "ab_chain.py"), "small", "64", "12"], capture_output=True,
                          text=True, timeout=600, cwd=repo)
     assert out.returncode == 0 and "IDENTICAL" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
+def test_cli_word_timestamps_json(micro_dir, tmp_path, monkeypatch):
+    """`--word-timestamps True -f json`: every segment of the written JSON carries its words."""
+    from whisper_mlx_b200.cli import main
+
+    wav = str(tmp_path / "in.wav")
+    _write_wav(wav, synth.long_audio(35.0, 6))
+    monkeypatch.chdir(tmp_path)
+    main([wav, "-f", "json", "--output-name", "out", "--model", micro_dir, "--condition-on-previous-text", "False",
+          "--word-timestamps", "True", "--verbose", "False", "--temperature-increment-on-fallback", "None", "--language", "en"])
+    r = json.load(open(tmp_path / "out.json"))
+    assert len(r["segments"]) >= 1 and all("words" in s for s in r["segments"])
+    words = [w for s in r["segments"] for w in s["words"]]
+    assert len(words) >= 1 and all({"word", "start", "end", "probability"} <= set(w) for w in words)
