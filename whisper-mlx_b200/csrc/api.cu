@@ -180,8 +180,8 @@ static int gemm(const void* A, long long lda, int M, const void* W, int N, int K
 // launches, so the work is spread over as many CTAs as fit in one wave.
 // Split-K plan of a <= 128-row GEMM: `workers` CTAs (or clusters of `group` CTAs in the multicast chain, each cluster
 // taking `group` neighbouring column tiles of one K range) share N / bn column tiles x s K slices.
-static int plan_split_k(int N, int K, int bn, int group = 1, int workers = 0) {
-  const int tiles = ceil_div(ceil_div(N, bn), group), num_kb = ceil_div(K, 64);
+static int plan_split_k(int N, int K, int bn, int group = 1, int workers = 0, int tiles_m = 1) {
+  const int tiles = ceil_div(ceil_div(N, bn), group) * tiles_m, num_kb = ceil_div(K, 64);
   if (workers <= 0) workers = device_sm_count();
   int s = workers / tiles;
   if (s > 8) s = 8;
@@ -308,10 +308,10 @@ static size_t carve_decoder(const b200w_dims& dm, int n_seq, int n_q, Carver& c,
   void* qc = c.take(rows * d * 2);
   void* mlp = c.take(rows * 4 * d * 2);
   float *pq = nullptr, *p1 = nullptr, *pr = nullptr;
-  if (rows <= 128) {
-    pq = static_cast<float*>(c.take((size_t)kMaxSplit * 128 * 3 * d * 4));
-    p1 = static_cast<float*>(c.take((size_t)kMaxSplit * 128 * d * 4));
-    pr = static_cast<float*>(c.take((size_t)kMaxSplit * 128 * d * 4));
+  if (rows <= 256) {  // (rows is already a multiple of 128)
+    pq = static_cast<float*>(c.take((size_t)kMaxSplit * rows * 3 * d * 4));
+    p1 = static_cast<float*>(c.take((size_t)kMaxSplit * rows * d * 4));
+    pr = static_cast<float*>(c.take((size_t)kMaxSplit * rows * d * 4));
   }
   unsigned int* counters = static_cast<unsigned int*>(c.take(kChainCounters * sizeof(unsigned int)));
   if (o) *o = DecBufs{x, h, qkv, att, qc, mlp, pq, p1, pr, counters};
@@ -644,17 +644,20 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   float* x = static_cast<float*>(bf.x);
   B200W_TRY(launch_embed(st->tokens, st->tokens_ld, st->pos, B, n_q, (const __nv_bfloat16*)m.w.tok_emb,
                          (const __nv_bfloat16*)m.w.dec_pos, d, dm.n_text_ctx, x, stream));
-  const bool small = rows <= 128 && n_q == 1;  // decode steps: split-K GEMMs whose reduction is fused into the consumers
+  // decode steps: split-K GEMMs whose reduction is fused into the consumers; the chain handles one or two row tiles
+  const bool chained = n_q == 1 && rows <= 256 && chain_enabled() && 2 * dm.n_text_layer + 2 <= kChainCounters;
+  const bool small = n_q == 1 && (rows <= 128 || chained);
+  const int rows_pad = ((rows + 127) / 128) * 128;
   // while sampling, sequences that have emitted EOT stop streaming their K/V (their tokens are forced to EOT by K9)
   const int* done = select ? st->finished : nullptr;
-  if (small && chain_enabled() && rows <= device_sm_count() && 2 * dm.n_text_layer + 2 <= kChainCounters) {
+  if (small && chained) {
     // K11: the small-M phases between the attention kernels run as three chains per layer
     //   [LN -> QKV]  SA  [out -> LN -> q]  CA  [out -> LN -> MLP1 -> MLP2 -> LN -> next layer's QKV]
-    const long long s3 = 128ll * 3 * d, s1 = 128ll * d;
+    const long long s3 = (long long)rows_pad * 3 * d, s1 = (long long)rows_pad * d;
     const bool mcp = use_mc_plan(rows, d);
-    const int grp = mcp ? 4 : 1, wk = mcp ? chain_mc_grid() / 4 : 0;
-    const int sp_qkv = plan_split_k(3 * d, d, 64, grp, wk), sp_d = plan_split_k(d, d, 64, grp, wk),
-              sp_mlp2 = plan_split_k(d, 4 * d, 64, grp, wk);
+    const int grp = mcp ? 4 : 1, wk = mcp ? chain_mc_grid() / 4 : 0, tm = rows_pad / 128;
+    const int sp_qkv = plan_split_k(3 * d, d, 64, grp, wk, tm), sp_d = plan_split_k(d, d, 64, grp, wk, tm),
+              sp_mlp2 = plan_split_k(d, 4 * d, 64, grp, wk, tm);
     B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, kChainCounters * sizeof(unsigned int), stream));
     int n_chain = 0;
     __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(bf.h);

@@ -143,11 +143,11 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
   int pre_cnt = 0, pre_stage0 = 0;
   auto prefetch_w = [&](const ChainPhase& Q) {
     const CUtensorMap* qb = &maps.b[Q.map];
-    const int q_tiles = (Q.tiles_n / kGroup) * Q.split_k;
+    const int q_tiles = (Q.tiles_n / kGroup) * p.tiles_m * Q.split_k;
     pre_stage0 = stage;
     pre_cnt = 0;
     for (int tile = worker; tile < q_tiles && pre_cnt < kChStages; tile += n_workers) {
-      const int ks = tile % Q.split_k, nt = (tile / Q.split_k) * kGroup + crank;
+      const int ks = tile % Q.split_k, nt = (tile / Q.split_k / p.tiles_m) * kGroup + crank;
       const int kb_end = min(Q.num_kb, (ks + 1) * Q.kb_per_split);
       for (int kb = ks * Q.kb_per_split; kb < kb_end && pre_cnt < kChStages; ++kb, ++pre_cnt) {
         mbar_wait(&empty_bar[stage], ring_phase ^ 1);
@@ -164,32 +164,34 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
   for (int ph = 0; ph < p.n_phases; ++ph) {
     const ChainPhase& P = p.ph[ph];
     if (P.kind == kChainGemm) {
-      const int num_tiles = (P.tiles_n / kGroup) * P.split_k;  // work items of this CTA's group
+      // work items of this CTA's group: (column tile [group], row tile, K slice), K slice fastest
+      const int num_tiles = (P.tiles_n / kGroup) * p.tiles_m * P.split_k;
       const CUtensorMap* ta = MC ? &maps.a4[P.map] : &maps.a[P.map];
       const CUtensorMap* tb = &maps.b[P.map];
       if (warp == 0) {
         if (lane == 0) {
           int item = 0;
-          auto load_a = [&](int slot, int kb) {  // the whole A tile, or this CTA's quarter of it for the whole cluster
+          auto load_a = [&](int slot, int kb, int mt) {  // the whole A tile, or this CTA's quarter of it for the cluster
             unsigned char* sa = smem + slot * kChStageBytes;
             if constexpr (MC)
-              tma_load_3d_mc(sa + crank * (kChABytes / kChCluster), ta, &full_bar[slot], kb * kChBK, crank * (kChBM / kChCluster), 0,
-                             kMask);
+              tma_load_3d_mc(sa + crank * (kChABytes / kChCluster), ta, &full_bar[slot], kb * kChBK,
+                             mt * kChBM + crank * (kChBM / kChCluster), 0, kMask);
             else
-              tma_load_3d(sa, ta, &full_bar[slot], kb * kChBK, 0, 0);
+              tma_load_3d(sa, ta, &full_bar[slot], kb * kChBK, mt * kChBM, 0);
           };
           for (int tile = worker; tile < num_tiles; tile += n_workers) {
-            const int ks = tile % P.split_k, nt = (tile / P.split_k) * kGroup + crank;
+            const int ks = tile % P.split_k, rest = tile / P.split_k;
+            const int mt = rest % p.tiles_m, nt = (rest / p.tiles_m) * kGroup + crank;
             const int kb_end = min(P.num_kb, (ks + 1) * P.kb_per_split);
             for (int kb = ks * P.kb_per_split; kb < kb_end; ++kb, ++item) {
               if (item < pre_cnt) {  // W tile already in flight (issued before the grid barrier): only A is missing
-                load_a((pre_stage0 + item) % kChStages, kb);
+                load_a((pre_stage0 + item) % kChStages, kb, mt);
                 continue;
               }
               mbar_wait(&empty_bar[stage], ring_phase ^ 1);
               unsigned char* sa = smem + stage * kChStageBytes;
               mbar_expect_tx(&full_bar[stage], kChStageBytes);
-              load_a(stage, kb);
+              load_a(stage, kb, mt);
               tma_load_3d(sa + kChABytes, tb, &full_bar[stage], kb * kChBK, nt * kChBN, 0);
               if (++stage == kChStages) {
                 stage = 0;
@@ -237,10 +239,11 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         const int e = warp - 4;
         const int q = e & 3, hh = e >> 2;
         float* stg = reinterpret_cast<float*>(smem + kChStages * kChStageBytes + 256) + e * (32 * 33);
-        const int t0 = q * 32;
-        const int rows_here = min(32, p.rows - t0);
         for (int tile = worker; tile < num_tiles; tile += n_workers) {
-          const int ks = tile % P.split_k, nt = (tile / P.split_k) * kGroup + crank;
+          const int ks = tile % P.split_k, rest = tile / P.split_k;
+          const int mt = rest % p.tiles_m, nt = (rest / p.tiles_m) * kGroup + crank;
+          const int t0 = mt * kChBM + q * 32;
+          const int rows_here = min(32, p.rows - t0);
           mbar_wait(&tmem_full_bar[acc], acc_phase);
           tcgen05_fence_after();
           const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kChBN;
@@ -280,9 +283,9 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         }
       }
     } else {
-      // residual + LayerNorm, one row per CTA (rows <= gridDim.x): thread t < d / 4 owns four consecutive features
-      const int row = blockIdx.x;
-      if (row < p.rows) {
+      // residual + LayerNorm, a row per CTA and round (rows <= 2 x grid): thread t < d / 4 owns four consecutive features
+      for (int row = blockIdx.x; row < p.rows; row += gridDim.x) {
+        __syncthreads();  // s_red is reused by the next row
         const int d = P.d;
         const bool on = tid < d / 4;
         const long long off = (long long)row * d + tid * 4;
@@ -387,7 +390,8 @@ int chain_mc_grid() {
 int chain_add_gemm(ChainMaps* maps, ChainParams* p, const void* A, long long lda, const void* W, int N, int K, int split_k,
                    void* out, long long ldc, long long split_stride, const float* bias, bool gelu) {
   B200W_CHECK_ARG(p->n_phases < kChainMaxPhases && p->n_gemm < kChainMaxGemm, "chain: too many phases");
-  B200W_CHECK_ARG(N % kChBN == 0 && K % kChBK == 0 && p->rows > 0 && p->rows <= kChBM, "chain: unsupported GEMM shape");
+  B200W_CHECK_ARG(N % kChBN == 0 && K % kChBK == 0 && p->rows > 0 && p->rows <= 2 * kChBM, "chain: unsupported GEMM shape");
+  p->tiles_m = ceil_div(p->rows, kChBM);
   B200W_CHECK_ARG(!gelu || (split_k <= 1 && bias != nullptr), "chain: GELU phase cannot be split");
   B200W_CHECK_ARG(gelu || ((ldc & 3) == 0 && (split_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0),
                   "chain: partial slabs must be 16-byte aligned");
@@ -438,10 +442,9 @@ int chain_add_ln(ChainParams* p, float* x, const float* part, int n_split, long 
 
 int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream) {
   B200W_CHECK_ARG(p.n_phases > 0 && p.counter != nullptr, "chain: empty chain or no barrier counter");
-  B200W_CHECK_ARG(p.rows <= device_sm_count(), "chain: one LayerNorm row per CTA needs rows <= SM count");
   B200W_TRY(init_chain());
   // the multicast form needs every GEMM phase to have a multiple of 4 column tiles and a grid that holds the rows
-  bool mc = g_chain_mc_grid >= p.rows && g_chain_mc_grid > 0;
+  bool mc = g_chain_mc_grid > 0;
   for (int i = 0; i < p.n_phases; ++i)
     if (p.ph[i].kind == kChainGemm && p.ph[i].tiles_n % kChCluster != 0) mc = false;
   cudaLaunchConfig_t cfg{};

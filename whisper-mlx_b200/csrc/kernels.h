@@ -85,6 +85,7 @@ struct ChainPhase {
 };
 struct ChainParams {
   int n_phases, n_gemm, rows;
+  int tiles_m;            // 128-row tiles (1 or 2), set by chain_add_gemm
   unsigned int* counter;  // zero on entry; one per launch
   ChainPhase ph[kChainMaxPhases];
 };
