@@ -295,8 +295,11 @@ struct DecBufs {
   void *x, *h, *qkv, *att, *qc, *mlp;
   float *part_qkv, *part_q, *part_res;  // split-K partial slabs (decode steps with <= 128 rows)
   unsigned int* counters;               // grid-barrier counters of the chain launches of one step
+  float* ca_part;                       // key-split cross-attention (small batches): per-chunk (max, sum, output)
+  int* ca_cnt;                          // ... and its arrival counters
 };
 constexpr int kChainCounters = 256;
+constexpr int kCaSplitUnits = 80;       // the key-split form is only used while (sequence, head) pairs <= SMs / 2
 constexpr int kMaxSplit = 8;
 static size_t carve_decoder(const b200w_dims& dm, int n_seq, int n_q, Carver& c, DecBufs* o) {
   const size_t d = dm.n_text_state;
@@ -314,7 +317,9 @@ static size_t carve_decoder(const b200w_dims& dm, int n_seq, int n_q, Carver& c,
     pr = static_cast<float*>(c.take((size_t)kMaxSplit * rows * d * 4));
   }
   unsigned int* counters = static_cast<unsigned int*>(c.take(kChainCounters * sizeof(unsigned int)));
-  if (o) *o = DecBufs{x, h, qkv, att, qc, mlp, pq, p1, pr, counters};
+  float* ca_part = static_cast<float*>(c.take((size_t)kCaSplitUnits * 8 * 66 * sizeof(float)));
+  int* ca_cnt = static_cast<int*>(c.take(kCaSplitUnits * sizeof(int)));
+  if (o) *o = DecBufs{x, h, qkv, att, qc, mlp, pq, p1, pr, counters, ca_part, ca_cnt};
   return c.off;
 }
 
@@ -650,6 +655,11 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   const int rows_pad = ((rows + 127) / 128) * 128;
   // while sampling, sequences that have emitted EOT stop streaming their K/V (their tokens are forced to EOT by K9)
   const int* done = select ? st->finished : nullptr;
+  // small batches (the exact sequential mode decodes one window at a time): the cross-attention splits its keys
+  const bool ca_split = B * n_q * H <= kCaSplitUnits && cross_attention_kv_splits(B, n_q, H) > 1;
+  float* kvp = ca_split ? bf.ca_part : nullptr;
+  int* kvc = ca_split ? bf.ca_cnt : nullptr;
+  if (ca_split) B200W_CUDA_OK(cudaMemsetAsync(bf.ca_cnt, 0, kCaSplitUnits * sizeof(int), stream));
   if (small && chained) {
     // K11: the small-M phases between the attention kernels run as three chains per layer
     //   [LN -> QKV]  SA  [out -> LN -> q]  CA  [out -> LN -> MLP1 -> MLP2 -> LN -> next layer's QKV]
@@ -690,7 +700,8 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
         B200W_TRY(launch_chain(maps, cp, stream));
       }
       B200W_TRY(launch_decoder_cross_attention(nullptr, B, 1, H, ckv, (long long)T * 2 * d, T, st->cross_slot,
-                                               (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq, done));
+                                               (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq, done, nullptr, kvp,
+                                               kvc));
       {
         const bool last = l + 1 == dm.n_text_layer;
         ChainMaps maps;
@@ -734,7 +745,8 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
                                       (__nv_bfloat16*)bf.h, stream));
       B200W_TRY(gemm_splitk(bf.h, d, rows, L.w_cq, d, d, bf.part_q, d, s1, sp_d, bn, stream, "dec_gemm_cq"));
       B200W_TRY(launch_decoder_cross_attention(nullptr, B, 1, H, ckv, (long long)T * 2 * d, T, st->cross_slot,
-                                               (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq, done));
+                                               (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq, done, nullptr, kvp,
+                                               kvc));
       B200W_TRY(gemm_splitk(bf.att, d, rows, L.w_cout, d, d, bf.part_res, d, s1, sp_d, bn, stream, "dec_gemm_cout"));
       B200W_TRY(launch_resid_ln_small(x, bf.part_res, sp_d, s1, L.b_cout, L.mlp_ln_g, L.mlp_ln_b, rows, d,
                                       (__nv_bfloat16*)bf.h, stream));
@@ -760,7 +772,8 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
       B200W_TRY(launch_layernorm(x, L.cross_ln_g, L.cross_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
       B200W_TRY(gemm(bf.h, d, rows, L.w_cq, d, d, bf.qc, d, false, L.b_cq, false, nullptr, 0, 0, stream));
       B200W_TRY(launch_decoder_cross_attention((const __nv_bfloat16*)bf.qc, B, n_q, H, ckv, (long long)T * 2 * d, T,
-                                               st->cross_slot, (__nv_bfloat16*)bf.att, stream, nullptr, 0, 0, nullptr, done));
+                                               st->cross_slot, (__nv_bfloat16*)bf.att, stream, nullptr, 0, 0, nullptr, done, nullptr,
+                                               kvp, kvc));
       B200W_TRY(gemm(bf.att, d, rows, L.w_cout, d, d, x, d, true, L.b_cout, false, x, d, 0, stream));
       B200W_TRY(launch_layernorm(x, L.mlp_ln_g, L.mlp_ln_b, rows, d, (__nv_bfloat16*)bf.h, nullptr, stream));
       B200W_TRY(gemm(bf.h, d, rows, L.w_mlp1, 4 * d, d, bf.mlp, 4 * d, false, L.b_mlp1, true, nullptr, 0, 0, stream));

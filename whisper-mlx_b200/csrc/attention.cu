@@ -609,14 +609,20 @@ constexpr int kCrossUnroll = B200W_CROSS_UNROLL;
 // kProbs: also store the attention probabilities (f32, [b][qi][h][T]) -- the cross-attention weights the word-level
 // alignment reads (UPSTREAM timing.py: softmax of the captured QK).  A separate instantiation: the decode-step
 // kernel is sensitive to every extra instruction in its prologue (section on kCrossUnroll above).
-template <bool kProbs>
+// kSplit (small batches, e.g. the batch-1 steps of the exact sequential mode): n_seq x n_head CTAs cannot fill the GPU,
+// so the keys of one (sequence, head) are cut into kv_splits chunks handled by different CTAs; each writes
+// (max, sum, unnormalised output) and the last one to arrive merges the chunks (self-resetting arrival counter).
+constexpr int kCrossPartFloats = 2 + kHd;
+
+template <bool kProbs, bool kSplit>
 __global__ void __launch_bounds__(kCrossThreads)
 decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int n_head,
-                               const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride, int T,
+                               const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride, int T_all,
                                const int* __restrict__ slot, __nv_bfloat16* __restrict__ out,
                                const float* __restrict__ part, int n_split, long long split_stride,
                                const float* __restrict__ bias, const int* __restrict__ finished,
-                               float* __restrict__ probs_out) {
+                               float* __restrict__ probs_out, int kv_splits, float* __restrict__ kv_part,
+                               int* __restrict__ kv_cnt) {
   __shared__ float s_p[kMaxCrossKeys];
   __shared__ float s_red[kCrossWarps];
   __shared__ float s_part[kCrossWarps][kHd];
@@ -627,11 +633,20 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   const int d = n_head * kHd;
   const long long ld = 2ll * d;  // K | V interleaved per row
   // queries of one (sequence, head) are adjacent CTAs: they stream the same K/V rows and share them through L2
-  const int qi = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qi = blockIdx.x, b = blockIdx.z;
+  const int h = kSplit ? (int)blockIdx.y / kv_splits : (int)blockIdx.y;
+  const int chunk = kSplit ? (int)blockIdx.y - h * kv_splits : 0;
   pdl_wait();
   pdl_launch_dependents();  // after the wait: at most one dependent grid is resident ahead of the running one
   if (finished != nullptr && finished[b]) return;  // no K/V streaming for sequences that have emitted EOT
-  const __nv_bfloat16* kbase = cross_kv + (long long)slot[b] * seq_stride + h * kHd + sub * 8;
+  // key range of this CTA: everything, or chunk `chunk` of kv_splits (multiples of 32 keys)
+  int k0 = 0, T = T_all;
+  if constexpr (kSplit) {
+    const int per = ((T_all + kv_splits - 1) / kv_splits + 31) & ~31;
+    k0 = min(chunk * per, T_all);
+    T = min(per, T_all - k0);
+  }
+  const __nv_bfloat16* kbase = cross_kv + (long long)slot[b] * seq_stride + (long long)k0 * ld + h * kHd + sub * 8;
   const __nv_bfloat16* vbase = kbase + d;
 
   float qv[8];
@@ -752,30 +767,82 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
     for (int i = 0; i < 8; ++i) s_part[warp][sub * 8 + i] = acc[i];
   }
   __syncthreads();
-  if (tid < kHd) {
-    float v = 0.0f;
+  if constexpr (!kSplit) {
+    if (tid < kHd) {
+      float v = 0.0f;
 #pragma unroll
-    for (int w = 0; w < kCrossWarps; ++w) v += s_part[w][tid];
-    out[((long long)b * n_q + qi) * d + h * kHd + tid] = __float2bfloat16(v / sum);
+      for (int w = 0; w < kCrossWarps; ++w) v += s_part[w][tid];
+      out[((long long)b * n_q + qi) * d + h * kHd + tid] = __float2bfloat16(v / sum);
+    }
+  } else {
+    __shared__ int s_last;
+    const int unit = (b * n_q + qi) * n_head + h;
+    float* mine = kv_part + ((long long)unit * kv_splits + chunk) * kCrossPartFloats;
+    if (tid < kHd) {
+      float v = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kCrossWarps; ++w) v += s_part[w][tid];
+      mine[2 + tid] = v;
+    }
+    if (tid == 0) {
+      mine[0] = (T > 0) ? mx : -INFINITY;  // an empty chunk contributes nothing
+      mine[1] = (T > 0) ? sum : 0.0f;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(kv_cnt + unit, 1) == kv_splits - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {  // every chunk of this (sequence, head, query) is in memory: merge
+      __threadfence();
+      if (tid < kHd) {
+        const float* all = kv_part + (long long)unit * kv_splits * kCrossPartFloats;
+        float M = -INFINITY;
+        for (int c2 = 0; c2 < kv_splits; ++c2) M = fmaxf(M, __ldcg(all + c2 * kCrossPartFloats));
+        float L = 0.0f, o = 0.0f;
+        for (int c2 = 0; c2 < kv_splits; ++c2) {
+          const float w2 = fast_exp2(__ldcg(all + c2 * kCrossPartFloats) - M);
+          L = fmaf(__ldcg(all + c2 * kCrossPartFloats + 1), w2, L);
+          o = fmaf(__ldcg(all + c2 * kCrossPartFloats + 2 + tid), w2, o);
+        }
+        out[((long long)b * n_q + qi) * d + h * kHd + tid] = __float2bfloat16(o / L);
+      }
+      if (tid == 0) kv_cnt[unit] = 0;  // ready for the next launch
+    }
   }
+}
+
+int cross_attention_kv_splits(int n_seq, int n_q, int n_head) {
+  const long long units = (long long)n_seq * n_q * n_head;
+  const int s = (int)(device_sm_count() / (units > 0 ? units : 1));
+  return s >= 2 ? (s > 8 ? 8 : s) : 1;  // split only when the (sequence, head) CTAs leave most SMs idle
 }
 
 int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, int n_head,
                                    const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
                                    __nv_bfloat16* out, cudaStream_t stream, const float* part, int n_split,
-                                   long long split_stride, const float* bias, const int* finished, float* probs_out) {
+                                   long long split_stride, const float* bias, const int* finished, float* probs_out,
+                                   float* kv_part, int* kv_cnt) {
   B200W_CHECK_ARG(n_seq > 0 && n_seq <= 65535 && n_q > 0 && n_q <= 65535, "cross_attention: bad sizes");
   B200W_CHECK_ARG(n_split > 0 ? (part && bias) : (q != nullptr), "cross_attention: missing query input");
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
-  dim3 grid(n_q, n_head, n_seq);
+  const int kv_splits = (kv_part != nullptr && kv_cnt != nullptr && probs_out == nullptr) ? cross_attention_kv_splits(n_seq, n_q, n_head) : 1;
   ProfScope prof_("decoder_cross_attention", stream);
-  if (probs_out != nullptr)
-    B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel<true>, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head,
-                           cross_kv, seq_stride, T, slot, out, part, n_split, split_stride, bias, finished, probs_out));
-  else
-    B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel<false>, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head,
+  if (kv_splits > 1) {
+    dim3 grid(n_q, n_head * kv_splits, n_seq);
+    B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel<false, true>, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head,
                            cross_kv, seq_stride, T, slot, out, part, n_split, split_stride, bias, finished,
-                           static_cast<float*>(nullptr)));
+                           static_cast<float*>(nullptr), kv_splits, kv_part, kv_cnt));
+  } else {
+    dim3 grid(n_q, n_head, n_seq);
+    if (probs_out != nullptr)
+      B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel<true, false>, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head,
+                             cross_kv, seq_stride, T, slot, out, part, n_split, split_stride, bias, finished, probs_out, 1,
+                             static_cast<float*>(nullptr), static_cast<int*>(nullptr)));
+    else
+      B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel<false, false>, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head,
+                             cross_kv, seq_stride, T, slot, out, part, n_split, split_stride, bias, finished,
+                             static_cast<float*>(nullptr), 1, static_cast<float*>(nullptr), static_cast<int*>(nullptr)));
+  }
   count_launch();
   return kOk;
 }

@@ -131,7 +131,11 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
                                    const __nv_bfloat16* cross_kv, long long seq_stride, int T, const int* slot,
                                    __nv_bfloat16* out, cudaStream_t stream, const float* part = nullptr,
                                    int n_split = 0, long long split_stride = 0, const float* bias = nullptr,
-                                   const int* finished = nullptr, float* probs_out = nullptr);
+                                   const int* finished = nullptr, float* probs_out = nullptr,
+                                   // small batches: workspace for the key-split form (kv_part: n_seq * n_q * n_head * 8 *
+                                   // 66 floats; kv_cnt: n_seq * n_q * n_head ints, zero on first use) or null
+                                   float* kv_part = nullptr, int* kv_cnt = nullptr);
+int cross_attention_kv_splits(int n_seq, int n_q, int n_head);
 
 // ---------------------------------------------------------------------------------------- K12 word alignment
 // stats workspace: (2 * n_sel * n_frames + n_sel * n_tok) floats; heads: n_sel (layer-relative index, head) pairs
