@@ -106,3 +106,26 @@ def test_timestamp_rules_equal_hf():
             theirs = proc(torch.from_numpy(toks), torch.from_numpy(logits.copy())).numpy()
             assert np.array_equal(np.isneginf(ours), np.isneginf(theirs)), h
             assert np.array_equal(ours[~np.isneginf(ours)], theirs[~np.isneginf(theirs)])
+
+
+def test_alignment_primitives_match_hf():
+    """oracle.timing's median filter and DTW (restating mlx_whisper/timing.py) against the independent implementations
+    in transformers (`generation_whisper._median_filter`, `_dynamic_time_warping`): identical filter output and
+    identical alignment paths on random cost matrices."""
+    import numpy as np
+    import torch
+    from transformers.models.whisper import generation_whisper as G
+
+    from oracle import timing as OT
+
+    rng = np.random.default_rng(0)
+    for shape in ((2, 5, 60), (1, 3, 9), (4, 2, 1500)):
+        x = rng.standard_normal(shape).astype(np.float32)
+        assert np.array_equal(OT.median_filter(x, 7), G._median_filter(torch.from_numpy(x), 7).numpy())
+    for n, m in ((23, 180), (1, 40), (40, 41), (30, 500)):
+        cost = rng.standard_normal((n, m)).astype(np.float32)
+        ti, tj = OT.dtw(-cost)
+        hi, hj = G._dynamic_time_warping(-cost.astype(np.float64))
+        assert np.array_equal(ti, hi) and np.array_equal(tj, hj), (n, m)
+        assert ti[0] == 0 and tj[0] == 0 and ti[-1] == n - 1 and tj[-1] == m - 1
+        assert np.all(np.diff(ti) >= 0) and np.all(np.diff(tj) >= 0)
