@@ -29,11 +29,15 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
                compression_ratio_threshold: Optional[float] = 2.4, logprob_threshold: Optional[float] = -1.0,
                no_speech_threshold: Optional[float] = 0.6, condition_on_previous_text: bool = True,
                language: Optional[str] = None, task: str = "transcribe", policy: str = "fp32",
-               sample_len: Optional[int] = None, fixed_windows: bool = False):
+               sample_len: Optional[int] = None, fixed_windows: bool = False,
+               max_tail_rounds: int = 8):
     """Returns {"text", "segments", "language"}.
 
-    `fixed_windows=True` is the batched-mode contract of the product: the
-    seek always advances by one full 30 s window instead of by the last decoded timestamp.
+    `fixed_windows=True` is the batched-mode contract of the product (not a mode of the
+    reference): windows start at fixed 30 s strides instead of at the last decoded timestamp.  Where the reference
+    would re-seek (tokens left after the last closed timestamp pair) the leftover text becomes a segment ending at
+    the window end; if there is no leftover text the uncovered tail [last timestamp, window end) is decoded as a
+    window of its own before the next planned window (at most `max_tail_rounds` times per planned window).
     """
     ids = TokenIds(dims.n_vocab)
     mel = A.log_mel_spectrogram(audio, dims.n_mels, padding=A.N_SAMPLES)
@@ -74,9 +78,16 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
                 "tokens": toks, "temperature": result.temperature, "avg_logprob": result.avg_logprob,
                 "compression_ratio": result.compression_ratio, "no_speech_prob": result.no_speech_prob}
 
+    window_end = 0     # fixed-window mode: end of the planned window being decoded, and how many of its tails were taken
+    tail_rounds = 0
     while seek < content_frames:
         time_offset = seek * HOP / SR
         segment_size = min(N_FRAMES, content_frames - seek)
+        if fixed_windows:
+            if seek >= window_end:  # a new planned window
+                window_end = seek + segment_size
+                tail_rounds = 0
+            segment_size = window_end - seek
         segment_duration = segment_size * HOP / SR
         segment = torch.from_numpy(_pad_or_trim_frames(mel[seek: seek + segment_size]))[None]
         result = decode_with_fallback(segment)
@@ -89,6 +100,7 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
             if should_skip:
                 seek += segment_size
                 continue
+        window_start = seek
 
         current = []
         ts = tokens >= ids.timestamp_begin
@@ -106,10 +118,24 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
                 current.append(new_segment(time_offset + start_pos * time_precision,
                                            time_offset + end_pos * time_precision, sl, result))
                 last = cur
-            if single_ending or fixed_windows:
+            if single_ending:
                 seek += segment_size
-            else:
+            elif not fixed_windows:
                 seek += (int(tokens[last - 1]) - ids.timestamp_begin) * input_stride
+            else:
+                advance = (int(tokens[last - 1]) - ids.timestamp_begin) * input_stride
+                trailing = tokens[last:]
+                if any(int(t) < ids.eot for t in trailing):
+                    first = int(trailing[0])
+                    start_pos = first - ids.timestamp_begin if first >= ids.timestamp_begin else advance // input_stride
+                    current.append(new_segment(time_offset + start_pos * time_precision, time_offset + segment_duration,
+                                               trailing, result))
+                    seek += segment_size
+                elif advance > 0 and tail_rounds < max_tail_rounds:
+                    tail_rounds += 1
+                    seek += advance  # the tail [seek, window_end) is decoded next
+                else:
+                    seek += segment_size
         else:
             duration = segment_duration
             stamps = tokens[ts.nonzero()[0]]
@@ -122,6 +148,8 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
             if s["start"] == s["end"] or s["text"].strip() == "":
                 s["text"] = ""
                 s["tokens"] = []
+        for s in current:
+            s["seek"] = window_start
         all_segments.extend({"id": i, **s} for i, s in enumerate(current, start=len(all_segments)))
         all_tokens.extend(t for s in current for t in s["tokens"])
         if not condition_on_previous_text or result.temperature > 0.5:

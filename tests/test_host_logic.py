@@ -60,26 +60,17 @@ def test_suppress_set_matches_oracle():
 
 
 def _oracle_segments(tokens, seek, size, fixed):
-    """The oracle's segmentation, driven with a canned decode result."""
-    from oracle import decoding as OD, model as OM, transcribe as OT
+    """Expected segmentation of one window, restated from oracle/transcribe.py's loop body: returns
+    ([(start, end, tokens)], advance) in exact mode and ([...], tail or None) in the fixed-window contract."""
+    import numpy as _np
     from oracle.tokens import TokenIds
 
     ids = TokenIds(51866)
-    out = {}
-
-    class R:
-        pass
-
-    # replicate the loop body of oracle.transcribe for one window (same code path as its while-loop)
-    import types
-    import numpy as _np
-
-    res = OD.DecodingResult(tokens=list(tokens), text="", avg_logprob=-0.5, no_speech_prob=0.0, temperature=0.0, compression_ratio=1.0)
     toks = _np.array(tokens, dtype=_np.int64)
     ts = toks >= ids.timestamp_begin
     single_ending = ts[-2:].tolist() == [False, True]
     consecutive = _np.where(_np.logical_and(ts[:-1], ts[1:]))[0] + 1
-    segs, adv = [], None
+    segs, adv, tail = [], None, None
     t0 = seek * 160 / 16000
     if len(consecutive) > 0:
         slices = consecutive.tolist()
@@ -90,7 +81,14 @@ def _oracle_segments(tokens, seek, size, fixed):
             sl = toks[last:cur]
             segs.append((t0 + (int(sl[0]) - ids.timestamp_begin) * 0.02, t0 + (int(sl[-1]) - ids.timestamp_begin) * 0.02, sl.tolist()))
             last = cur
-        adv = size if (single_ending or fixed) else (int(toks[last - 1]) - ids.timestamp_begin) * 2
+        adv = size if single_ending else (int(toks[last - 1]) - ids.timestamp_begin) * 2
+        if fixed and not single_ending:
+            trailing = toks[last:].tolist()
+            if any(t < ids.eot for t in trailing):
+                start = trailing[0] - ids.timestamp_begin if trailing[0] >= ids.timestamp_begin else adv // 2
+                segs.append((t0 + start * 0.02, t0 + size * 0.01, trailing))
+            elif adv > 0:
+                tail = (seek + adv, size - adv)
     else:
         dur = size * 160 / 16000
         stamps = toks[ts.nonzero()[0]]
@@ -98,38 +96,51 @@ def _oracle_segments(tokens, seek, size, fixed):
             dur = (int(stamps[-1]) - ids.timestamp_begin) * 0.02
         segs.append((t0, t0 + dur, toks.tolist()))
         adv = size
-    return segs, adv
+    return segs, (tail if fixed else adv)
 
 
 @pytest.mark.parametrize("fixed", [False, True])
 def test_segmentation_matches_oracle(fixed):
     from whisper_mlx_b200.decoding import DecodingResult
     from whisper_mlx_b200.tokenizer import get_tokenizer
-    from whisper_mlx_b200.transcribe import _segments_for_window
+    from whisper_mlx_b200.transcribe import _clear_empty_segments, _segments_fixed_window, _segments_for_window
 
     tk = get_tokenizer(True, num_languages=100, language="en", task="transcribe")
     tb = tk.timestamp_begin
     streams = [
-        [tb, 10, 11, tb + 100, tb + 100, 12, tb + 250, tb + 250, 13, 14],   # unfinished tail: seek to the last pair
+        [tb, 10, 11, tb + 100, tb + 100, 12, tb + 250, tb + 250, 13, 14],   # unfinished tail text: seek to the last pair / keep it
+        [tb, 10, 11, tb + 100, tb + 100, 12, tb + 250, tb + 250],           # closes early, nothing after: re-seek / tail window
+        [tb, 10, tb + 1350, tb + 1350, tb + 1400],                          # ... with only an opening timestamp after the pair
         [tb + 5, 10, tb + 1500],                                           # single timestamp ending
         [tb, 10, 11, 12],                                                   # no closing timestamp
         [tb + 20, 7, tb + 60, tb + 60, 8, tb + 90],                         # pair then single ending
-        [tb, tb],                                                           # empty pair
+        [tb, tb],                                                           # empty pair at 0: no progress possible
         [10, 11, 12],
+        [],
     ]
     for s in streams:
         res = DecodingResult(audio_features=None, language="en", tokens=s, avg_logprob=-0.5, no_speech_prob=0.0, temperature=0.0,
                              compression_ratio=1.0)
-        segs, adv, _ = _segments_for_window(np.array(s, dtype=np.int64), 3000, 3000, res, tk, 2, 0.02, not fixed)
-        ref, ref_adv = _oracle_segments(s, 3000, 3000, fixed)
-        assert adv == ref_adv, s
+        toks = np.array(s, dtype=np.int64)
+        if fixed:
+            segs, got2 = _segments_fixed_window(toks, 3000, 3000, res, tk, 2, 0.02)
+        else:
+            segs, got2, _, _ = _segments_for_window(toks, 3000, 3000, res, tk, 2, 0.02)
+        _clear_empty_segments(segs, with_words=False)
+        ref, ref2 = _oracle_segments(s, 3000, 3000, fixed)
+        assert got2 == ref2, (s, got2, ref2)
         assert len(segs) == len(ref)
-        for g, (st, en, toks) in zip(segs, ref):
+        for g, (st, en, toks_ref) in zip(segs, ref):
             assert abs(g["start"] - st) < 1e-9 and abs(g["end"] - en) < 1e-9
             if g["start"] != g["end"] and g["text"].strip():
-                assert g["tokens"] == toks
+                assert g["tokens"] == toks_ref
             else:
                 assert g["tokens"] == [] and g["text"] == ""
+    if fixed:
+        s = streams[1]
+        _, tail = _segments_fixed_window(np.array(s, dtype=np.int64), 3000, 3000,
+                                         DecodingResult(audio_features=None, language="en", tokens=s), tk, 2, 0.02)
+        assert tail == (3000 + 500, 2500)
 
 
 def test_writers(tmp_path):

@@ -230,12 +230,19 @@ class DecodeSession:
             GRAPH_KERNEL_LAUNCHES += n
 
 
+def _vocab_dir(model) -> Optional[str]:
+    return getattr(model, "model_path", None)
+
+
 class DecodingTask:
-    def __init__(self, model, options: DecodingOptions):
+    def __init__(self, model, options: DecodingOptions, tokenizer: Optional[Tokenizer] = None):
+        """`tokenizer`: the caller's tokenizer (transcribe() passes its own so that segment text, DecodingResult.text
+        and the compression ratio all come from one vocabulary); default: built for the model's directory."""
         self.model = model
         language = options.language or "en"
-        tokenizer = get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language=language,
-                                  task=options.task)
+        if tokenizer is None:
+            tokenizer = get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language=language,
+                                      task=options.task, vocab_dir=_vocab_dir(model))
         self.tokenizer: Tokenizer = tokenizer
         self.options: DecodingOptions = self._verify_options(options)
 
@@ -412,7 +419,7 @@ def decode(model, mel: torch.Tensor, options: DecodingOptions = DecodingOptions(
         options = replace(options, **kwargs)
     if options.language is None:
         lang_tokens, lang_probs = detect_language(model, mel)
-        tk = get_tokenizer(model.is_multilingual, num_languages=model.num_languages)
+        tk = get_tokenizer(model.is_multilingual, num_languages=model.num_languages, vocab_dir=_vocab_dir(model))
         codes = [tk.language_code(t) for t in lang_tokens]
         # the reference decodes each window with its own language; batches here share one prompt
         if len(set(codes)) > 1:
@@ -431,7 +438,7 @@ def detect_language(model, mel: torch.Tensor, tokenizer: Optional[Tokenizer] = N
     Returns (language_tokens list[int], language_probs list[dict]); scalars for a single window.
     """
     if tokenizer is None:
-        tokenizer = get_tokenizer(model.is_multilingual, num_languages=model.num_languages)
+        tokenizer = get_tokenizer(model.is_multilingual, num_languages=model.num_languages, vocab_dir=_vocab_dir(model))
     if tokenizer.language is None or tokenizer.language_token not in tokenizer.sot_sequence:
         raise ValueError("This model doesn't have language tokens so it can't perform lang id")
     mel = torch.as_tensor(mel)

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import json
 from pathlib import Path
-from typing import Dict
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -57,8 +57,8 @@ def dequantize_weights(weights: Dict[str, torch.Tensor], group_size: int = 64, b
     return out
 
 
-def load_model(path_or_hf_repo: str, dtype: torch.dtype = torch.bfloat16, device=None) -> Whisper:
-    """Load a Whisper model from a local directory or a Hugging Face repo id (MLX-format weights)."""
+def resolve_model_path(path_or_hf_repo: str) -> Path:
+    """A local directory, or the snapshot of a Hugging Face repo id (downloaded or already cached)."""
     model_path = Path(path_or_hf_repo)
     if not model_path.exists():
         try:
@@ -68,7 +68,13 @@ def load_model(path_or_hf_repo: str, dtype: torch.dtype = torch.bfloat16, device
         except Exception as e:  # noqa: BLE001 - offline / unknown repo
             raise FileNotFoundError(
                 f"{path_or_hf_repo!r} is neither a local directory nor a downloadable Hugging Face repo ({e})") from e
+    return model_path
 
+
+def read_model_files(model_path) -> Tuple[ModelDimensions, Dict[str, torch.Tensor], Optional[np.ndarray]]:
+    """The host half of `load_model`: `config.json` -> dims, `weights.safetensors` / `weights.npz` -> dense tensors under
+    the MLX parameter names (quantised triples expanded), and the optional `alignment_heads` table."""
+    model_path = Path(model_path)
     with open(str(model_path / "config.json"), "r") as f:
         config = json.loads(f.read())
         config.pop("model_type", None)
@@ -79,8 +85,17 @@ def load_model(path_or_hf_repo: str, dtype: torch.dtype = torch.bfloat16, device
         weights = dequantize_weights(weights, int(quantization.get("group_size", 64)), int(quantization.get("bits", 4)))
     alignment_heads = weights.pop("alignment_heads", None)
     weights = {k: v for k, v in weights.items() if not k.endswith("encoder.positional_embedding")}
-    model = Whisper(model_args, weights, device=device, dtype=dtype)
     if alignment_heads is not None:  # (n, 2) [layer, head] pairs used by word-level timestamps
-        model.alignment_heads = np.asarray(alignment_heads.cpu().numpy(), dtype=np.int64).reshape(-1, 2)
+        alignment_heads = np.asarray(alignment_heads.cpu().numpy(), dtype=np.int64).reshape(-1, 2)
+    return model_args, weights, alignment_heads
+
+
+def load_model(path_or_hf_repo: str, dtype: torch.dtype = torch.bfloat16, device=None) -> Whisper:
+    """Load a Whisper model from a local directory or a Hugging Face repo id (MLX-format weights)."""
+    model_path = resolve_model_path(path_or_hf_repo)
+    model_args, weights, alignment_heads = read_model_files(model_path)
+    model = Whisper(model_args, weights, device=device, dtype=dtype)
+    if alignment_heads is not None:
+        model.alignment_heads = alignment_heads
     model.model_path = str(model_path)
     return model

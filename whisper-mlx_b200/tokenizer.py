@@ -4,9 +4,11 @@ restated in SURVEY.md A.6 and Appendix B.2).
 The special-token table is computed exactly as the reference does (specials appended after the BPE
 ranks in a fixed order).  Text <-> ids needs the BPE vocabulary file (`multilingual.tiktoken` /
 `gpt2.tiktoken`), which the reference ships as a package asset; it is looked up in, in order,
-$B200W_TIKTOKEN_DIR, <this package>/assets/ and the model directory.  When it is not on disk (this
-image has no copy and no network) ids are rendered with a deterministic surrogate vocabulary so that the
-text / compression-ratio plumbing stays exercisable; token ids are unaffected.
+$B200W_TIKTOKEN_DIR, <this package>/assets/ and the model directory.  When it is not on disk the tokenizer
+REFUSES to be built (a transcript rendered from a made-up vocabulary must never reach a .txt file or a
+compression-ratio decision).  Only with B200W_ALLOW_SURROGATE=1 -- set by the test-suite and the benchmark,
+which run random-init weights and compare token ids -- are ids rendered with a deterministic surrogate
+vocabulary so that the text / compression-ratio plumbing stays exercisable; token ids are unaffected.
 """
 from __future__ import annotations
 
@@ -283,12 +285,27 @@ class Tokenizer:
         return words, word_tokens
 
 
+def surrogate_allowed() -> bool:
+    return os.environ.get("B200W_ALLOW_SURROGATE", "0") == "1"
+
+
 @lru_cache(maxsize=None)
+def _get_encoding(name: str, num_languages: int, vocab_path: Optional[str]) -> _Encoding:
+    return _Encoding(name, num_languages, vocab_path)
+
+
 def get_encoding(name: str = "gpt2", num_languages: int = 99, vocab_dir: Optional[str] = None) -> _Encoding:
-    return _Encoding(name, num_languages, _find_vocab(name, (vocab_dir,) if vocab_dir else ()))
+    path = _find_vocab(name, (vocab_dir,) if vocab_dir else ())
+    if path is None and not surrogate_allowed():
+        where = [os.environ.get("B200W_TIKTOKEN_DIR") or "$B200W_TIKTOKEN_DIR (unset)",
+                 os.path.join(os.path.dirname(__file__), "assets"), vocab_dir or "<model directory> (not given)"]
+        raise FileNotFoundError(
+            f"{name}.tiktoken (the BPE vocabulary mlx_whisper ships under mlx_whisper/assets/) was not found in "
+            f"{', '.join(where)}: text cannot be produced without it.  Copy the file into one of these directories.  "
+            "(B200W_ALLOW_SURROGATE=1 renders ids with a made-up vocabulary -- for tests and benchmarks only.)")
+    return _get_encoding(name, num_languages, path)
 
 
-@lru_cache(maxsize=None)
 def get_tokenizer(multilingual: bool, *, num_languages: int = 99, language: Optional[str] = None,
                   task: Optional[str] = None, vocab_dir: Optional[str] = None) -> Tokenizer:
     if language is not None:
@@ -307,4 +324,10 @@ def get_tokenizer(multilingual: bool, *, num_languages: int = 99, language: Opti
         language = None
         task = None
     encoding = get_encoding(name=encoding_name, num_languages=num_languages, vocab_dir=vocab_dir)
-    return Tokenizer(encoding=encoding, num_languages=num_languages, language=language, task=task)
+    key = (id(encoding), num_languages, language, task)
+    if key not in _TOKENIZERS:
+        _TOKENIZERS[key] = Tokenizer(encoding=encoding, num_languages=num_languages, language=language, task=task)
+    return _TOKENIZERS[key]
+
+
+_TOKENIZERS: Dict[tuple, Tokenizer] = {}

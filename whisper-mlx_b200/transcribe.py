@@ -8,8 +8,14 @@ Same signature, option names, thresholds and result dictionary.  Two execution m
   starts at the last decoded timestamp.  Bit-for-bit the reference control flow.
 * fixed-window batches (`window_batch=N`): the file is cut into back-to-back 30 s windows which are
   independent when `condition_on_previous_text=False` (the `./run` setting); N windows are encoded and
-  decoded together.  This is the throughput mode the benchmarks measure; segment
-  boundaries can differ from exact mode because the seek does not follow the decoded timestamps.
+  decoded together.  This is the throughput mode the benchmarks measure.  The
+  reference re-seeks to the last closed timestamp of a window, so that speech running across the window
+  end is decoded again by the next window; with fixed strides that audio would be lost.  Here no audio is
+  dropped: text left unfinished at the end of a window becomes a segment that ends at the window end, and
+  a window that closes its last segment early WITHOUT further text gets its uncovered tail
+  [last timestamp, window end) decoded as a window of its own in a follow-up batch (tails of one rank's
+  windows stay on that rank, so sharding needs no exchange).  Segment boundaries can still differ from
+  exact mode because window starts do not follow the decoded timestamps.
 """
 from __future__ import annotations
 
@@ -90,9 +96,23 @@ def _get_end(segments: List[dict]) -> Optional[float]:
                 segments[-1]["end"] if segments else None)
 
 
+def _clear_empty_segments(segments: List[dict], with_words: bool) -> None:
+    """If a segment is instantaneous or does not contain text, clear it (the reference does this once per window,
+    AFTER the word-timestamp pass)."""
+    for segment in segments:
+        if segment["start"] == segment["end"] or segment["text"].strip() == "":
+            segment["text"] = ""
+            segment["tokens"] = []
+            if with_words:
+                segment["words"] = []
+
+
 def _segments_for_window(tokens: np.ndarray, seek: int, segment_size: int, result: DecodingResult, tokenizer,
-                         input_stride: int, time_precision: float, follow_timestamps: bool):
-    """Split one window's tokens at consecutive timestamp pairs.  Returns (segments, seek advance)."""
+                         input_stride: int, time_precision: float):
+    """Split one window's tokens at consecutive timestamp pairs, exactly like the reference's loop body.
+
+    Returns (segments, seek advance, single_timestamp_ending, trailing): `trailing` are the tokens after the last closed
+    pair which the reference ignores because it re-seeks to that timestamp (empty when nothing is left over)."""
     time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
     segment_duration = segment_size * HOP_LENGTH / SAMPLE_RATE
 
@@ -104,6 +124,7 @@ def _segments_for_window(tokens: np.ndarray, seek: int, segment_size: int, resul
                 "compression_ratio": res.compression_ratio, "no_speech_prob": res.no_speech_prob}
 
     current_segments = []
+    trailing = tokens[:0]
     timestamp_tokens = tokens >= tokenizer.timestamp_begin
     single_timestamp_ending = timestamp_tokens[-2:].tolist() == [False, True]
     consecutive = np.where(np.logical_and(timestamp_tokens[:-1], timestamp_tokens[1:]))[0]
@@ -121,13 +142,14 @@ def _segments_for_window(tokens: np.ndarray, seek: int, segment_size: int, resul
                                                 end=time_offset + end_timestamp_pos * time_precision,
                                                 toks=sliced_tokens, res=result))
             last_slice = current_slice
-        if single_timestamp_ending or not follow_timestamps:
+        if single_timestamp_ending:
             # single timestamp at the end means no speech after the last timestamp
             advance = segment_size
         else:
             # otherwise, ignore the unfinished segment and seek to the last timestamp
             last_timestamp_pos = int(tokens[last_slice - 1]) - tokenizer.timestamp_begin
             advance = last_timestamp_pos * input_stride
+            trailing = tokens[last_slice:]
     else:
         duration = segment_duration
         timestamps = tokens[timestamp_tokens.nonzero()[0]]
@@ -137,12 +159,33 @@ def _segments_for_window(tokens: np.ndarray, seek: int, segment_size: int, resul
             duration = last_timestamp_pos * time_precision
         current_segments.append(new_segment(start=time_offset, end=time_offset + duration, toks=tokens, res=result))
         advance = segment_size
-    # if a segment is instantaneous or does not contain text, clear it
-    for segment in current_segments:
-        if segment["start"] == segment["end"] or segment["text"].strip() == "":
-            segment["text"] = ""
-            segment["tokens"] = []
-    return current_segments, advance, single_timestamp_ending
+    return current_segments, advance, single_timestamp_ending, trailing
+
+
+def _segments_fixed_window(tokens: np.ndarray, seek: int, segment_size: int, result: DecodingResult, tokenizer,
+                           input_stride: int, time_precision: float):
+    """Fixed-window mode: the reference's segmentation, then what it would have left to the next (re-seeked) window.
+
+    Returns (segments, tail): `tail` is None or the (seek, size) of the uncovered end of this window, to be decoded as
+    a window of its own (module docstring)."""
+    segs, advance, _, trailing = _segments_for_window(tokens, seek, segment_size, result, tokenizer, input_stride,
+                                                      time_precision)
+    tail = None
+    if advance < segment_size:  # the reference would re-seek to the last closed timestamp
+        if any(int(t) < tokenizer.eot for t in trailing):
+            # unfinished text: keep it, as a segment from its opening timestamp to the end of the window
+            time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
+            first = int(trailing[0])
+            start_pos = (first - tokenizer.timestamp_begin) if first >= tokenizer.timestamp_begin else advance // input_stride
+            toks = [int(t) for t in trailing]
+            segs.append({"seek": seek, "start": time_offset + start_pos * time_precision,
+                         "end": time_offset + segment_size * HOP_LENGTH / SAMPLE_RATE,
+                         "text": tokenizer.decode([t for t in toks if t < tokenizer.eot]), "tokens": toks,
+                         "temperature": result.temperature, "avg_logprob": result.avg_logprob,
+                         "compression_ratio": result.compression_ratio, "no_speech_prob": result.no_speech_prob})
+        elif advance > 0:
+            tail = (seek + advance, segment_size - advance)
+    return segs, tail
 
 
 def transcribe(
@@ -166,6 +209,8 @@ def transcribe(
     model=None,
     rank: int = 0,
     world_size: int = 1,
+    max_tail_rounds: int = 8,
+    _backend=None,
     **decode_options,
 ):
     """Transcribe an audio file (path, NumPy array or torch tensor of 16 kHz mono samples).
@@ -176,7 +221,9 @@ def transcribe(
     many windows go through one encoder call, `model` passes an already loaded `Whisper`; `rank` /
     `world_size` (batched mode, one process per GPU with torch.distributed initialised) make this process
     decode only its block of windows and gather the per-window segments on the host, so every rank returns
-    the full result.
+    the full result; `max_tail_rounds` bounds the follow-up batches that decode uncovered window tails
+    (0: never re-decode a tail).  `_backend` (tests only) replaces the device side -- log-mel, encoder and
+    decoder -- with a stand-in so that the control flow can be exercised on a CPU.
     """
     if word_timestamps and decode_options.get("task", "transcribe") == "translate" and verbose:
         warnings.warn("Word-level timestamps on translations may not be reliable.")
@@ -184,22 +231,39 @@ def transcribe(
         warnings.warn("--hallucination_silence_threshold requires --word_timestamps True; it has no effect")
 
     dtype = torch.bfloat16 if decode_options.get("fp16", True) else torch.float32
-    if model is None:
+    if _backend is not None:
+        model = _backend.model
+    elif model is None:
         model = ModelHolder.get_model(path_or_hf_repo, dtype)
     if window_batch is None:
         window_batch = int(os.environ.get("B200W_WINDOW_BATCH", "0"))
 
-    # whole-file log-mel with 30 s of zero padding; the clamp uses the file-wide maximum (K1 + K1b)
-    pcm = _to_device_audio(audio, model.device)
-    if pcm.ndim != 1:
-        raise ValueError("transcribe() takes one mono signal")
-    mel, gmax = log_mel_unclamped(pcm, n_mels=model.dims.n_mels, padding=N_SAMPLES)
-    mel2d = mel[0]
-    content_frames = mel2d.shape[-2] - N_FRAMES
-    content_duration = float(content_frames * HOP_LENGTH / SAMPLE_RATE)
+    if _backend is not None:
+        n_mel_frames = _backend.mel_frames(audio)
+        features_for = _backend.features
+        run_decode = _backend.decode
+    else:
+        # whole-file log-mel with 30 s of zero padding; the clamp uses the file-wide maximum (K1 + K1b)
+        pcm = _to_device_audio(audio, model.device)
+        if pcm.ndim != 1:
+            raise ValueError("transcribe() takes one mono signal")
+        mel, gmax = log_mel_unclamped(pcm, n_mels=model.dims.n_mels, padding=N_SAMPLES)
+        mel2d = mel[0]
+        n_mel_frames = mel2d.shape[-2]
 
-    def slabs_for(seeks: List[int], sizes: List[int]) -> torch.Tensor:
-        return model.mel_windows(mel2d, gmax, seeks, sizes, [0] * len(seeks))
+        def features_for(seeks: List[int], sizes: List[int]) -> torch.Tensor:
+            """Encoder states (n, 1500, d) of the windows starting at mel rows `seeks` with `sizes` valid frames."""
+            feats = []
+            for e0 in range(0, len(seeks), encoder_batch):
+                sk, sz = seeks[e0: e0 + encoder_batch], sizes[e0: e0 + encoder_batch]
+                feats.append(model.encode_slabs(model.mel_windows(mel2d, gmax, sk, sz, [0] * len(sk))))
+            return torch.cat(feats, 0) if len(feats) > 1 else feats[0]
+
+        def run_decode(features, options: DecodingOptions, tokenizer) -> List[DecodingResult]:
+            return DecodingTask(model, options, tokenizer=tokenizer).run_features(features)
+
+    content_frames = n_mel_frames - N_FRAMES
+    content_duration = float(content_frames * HOP_LENGTH / SAMPLE_RATE)
 
     if decode_options.get("language", None) is None:
         if not model.is_multilingual:
@@ -207,8 +271,8 @@ def transcribe(
         else:
             if verbose:
                 print("Detecting language using up to the first 30 seconds. Use the `language` decoding option to specify the language")
-            xa0 = model.encode_slabs(slabs_for([0], [min(N_FRAMES, mel2d.shape[-2])]))
-            _, probs = detect_language(model, xa0)
+            xa0 = features_for([0], [min(N_FRAMES, n_mel_frames)])
+            _, probs = _backend.detect_language(xa0) if _backend is not None else detect_language(model, xa0)
             decode_options["language"] = max(probs[0], key=probs[0].get)
             if verbose is not None:
                 print(f"Detected language: {LANGUAGES[decode_options['language']].title()}")
@@ -257,7 +321,7 @@ def transcribe(
         results: List[Optional[DecodingResult]] = [None] * n
         pending = list(range(n))
         for t in temperatures:
-            out = DecodingTask(model, options_for(float(t), prompt)).run_features(features[pending])
+            out = run_decode(features[pending], options_for(float(t), prompt), tokenizer)
             still = []
             for i, r in zip(pending, out):
                 results[i] = r
@@ -292,6 +356,8 @@ def transcribe(
         if verbose:
             for segment in current_segments:
                 print(f"[{_format_timestamp(segment['start'])} --> {_format_timestamp(segment['end'])}] {segment['text']}")
+        # the reference clears instantaneous / empty segments once per window, after the word pass and the printing
+        _clear_empty_segments(current_segments, with_words=word_timestamps)
         all_segments.extend({"id": i, **segment} for i, segment in enumerate(current_segments, start=len(all_segments)))
         all_tokens.extend(token for segment in current_segments for token in segment["tokens"])
 
@@ -306,26 +372,28 @@ def transcribe(
         # ---------------- fixed 30 s windows, window_batch at a time ----------------
         windows = plan_windows(content_frames, seek_clips, N_FRAMES)
         mine = shard_indices(len(windows), rank, world_size)  # all windows when world_size == 1
-        local = {}
-        for i0 in range(0, len(mine), window_batch):
-            idxs = mine[i0: i0 + window_batch]
-            chunk = [windows[i] for i in idxs]
-            feats = []
-            for e0 in range(0, len(chunk), encoder_batch):
-                sub = chunk[e0: e0 + encoder_batch]
-                feats.append(model.encode_slabs(slabs_for([w[0] for w in sub], [w[1] for w in sub])))
-            features = torch.cat(feats, 0) if len(feats) > 1 else feats[0]
-            results = decode_with_fallback(features, [])
-            for i, (seek, size), res in zip(idxs, chunk, results):
-                if should_skip(res):
-                    local[i] = None
-                    continue
-                tokens = np.array(res.tokens, dtype=np.int64)
-                segs, _, _ = _segments_for_window(tokens, seek, size, res, tokenizer, input_stride, time_precision, False)
-                local[i] = segs
+        local = {i: [] for i in mine}
+        pending = [(i, windows[i][0], windows[i][1]) for i in mine]  # (planned window, seek, size)
+        rounds = 0
+        while pending:
+            tails = []
+            for i0 in range(0, len(pending), window_batch):
+                chunk = pending[i0: i0 + window_batch]
+                features = features_for([c[1] for c in chunk], [c[2] for c in chunk])
+                results = decode_with_fallback(features, [])
+                for (i, seek, size), res in zip(chunk, results):
+                    if should_skip(res):
+                        continue
+                    tokens = np.array(res.tokens, dtype=np.int64)
+                    segs, tail = _segments_fixed_window(tokens, seek, size, res, tokenizer, input_stride, time_precision)
+                    local[i].extend(segs)
+                    if tail is not None and rounds < max_tail_rounds:
+                        tails.append((i, tail[0], tail[1]))
+            pending = tails  # uncovered window ends, decoded as windows of their own (a tail is shorter than its parent)
+            rounds += 1
         # host-side gather of the per-window segments (no device collective on the data path)
         for segs in gather_by_index(local, len(windows)) if world_size > 1 else [local[i] for i in range(len(windows))]:
-            if segs is not None:
+            if segs:
                 emit(segs)
     else:
         # ---------------- exact mode: the reference's sequential seek loop ----------------
@@ -341,7 +409,7 @@ def transcribe(
                     seek = seek_clips[clip_idx][0]
                 continue
             segment_size = min(N_FRAMES, content_frames - seek, seek_clip_end - seek)
-            features = model.encode_slabs(slabs_for([seek], [segment_size]))
+            features = features_for([seek], [segment_size])
             result = decode_with_fallback(features, all_tokens[prompt_reset_since:])[0]
             tokens = np.array(result.tokens, dtype=np.int64)
             if should_skip(result):
@@ -351,8 +419,8 @@ def transcribe(
             time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
             window_end_time = float((seek + N_FRAMES) * HOP_LENGTH / SAMPLE_RATE)
             segment_duration = segment_size * HOP_LENGTH / SAMPLE_RATE
-            segs, advance, single_timestamp_ending = _segments_for_window(tokens, seek, segment_size, result, tokenizer,
-                                                                          input_stride, time_precision, True)
+            segs, advance, single_timestamp_ending, _ = _segments_for_window(tokens, seek, segment_size, result, tokenizer,
+                                                                             input_stride, time_precision)
             seek += advance
             if word_timestamps:
                 last_speech_timestamp = add_word_timestamps(
@@ -407,12 +475,6 @@ def transcribe(
                 last_word_end = _get_end(segs)
                 if last_word_end is not None:
                     last_speech_timestamp = last_word_end
-                # the reference clears instantaneous / empty segments after the word pass
-                for segment in segs:
-                    if segment["start"] == segment["end"] or segment["text"].strip() == "":
-                        segment["text"] = ""
-                        segment["tokens"] = []
-                        segment["words"] = []
             emit(segs)
             if not condition_on_previous_text or result.temperature > 0.5:
                 # do not feed the prompt tokens if a high temperature was used
