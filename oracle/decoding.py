@@ -36,6 +36,8 @@ class DecodingResult:
     temperature: float = 0.0
     compression_ratio: float = float("nan")
     sum_logprob: float = float("nan")
+    # per sampled token: gap between the two best filtered logits (how close the greedy choice was to flipping)
+    margins: List[float] = field(default_factory=list)
 
 
 # ------------------------------------------------------------------------------ logit filters
@@ -164,6 +166,7 @@ def decode(w, dims: M.ModelDimensions, mel: torch.Tensor, *, language: str = "en
     gen = torch.Generator().manual_seed(seed)
     cache = None
     kept_logits = []
+    step_margins = []
     for i in range(sample_len):
         inp = tokens if i == 0 else tokens[:, -1:]
         logits, cache = M.decoder_forward(w, dims, torch.from_numpy(inp), xa, cache, policy=policy)
@@ -173,6 +176,8 @@ def decode(w, dims: M.ModelDimensions, mel: torch.Tensor, *, language: str = "en
         if return_logits:
             kept_logits.append(step.copy())
         filter_logits(step, tokens, sample_begin, ids, suppress, without_timestamps, max_init_idx, suppress_blank_)
+        top2 = torch.from_numpy(step).topk(2, dim=-1).values
+        step_margins.append((top2[:, 0] - top2[:, 1]).tolist())
         tokens, done = greedy_update(tokens, step, sum_lp, ids.eot, temperature, gen)
         if done or tokens.shape[-1] > n_ctx:
             break
@@ -185,7 +190,8 @@ def decode(w, dims: M.ModelDimensions, mel: torch.Tensor, *, language: str = "en
         results.append(DecodingResult(
             tokens=t, text=text, language=language, sum_logprob=float(sum_lp[b]),
             avg_logprob=float(sum_lp[b]) / (len(t) + 1), no_speech_prob=float(no_speech[b]),
-            temperature=temperature, compression_ratio=compression_ratio(text)))
+            temperature=temperature, compression_ratio=compression_ratio(text),
+            margins=[float(sm[b]) for sm in step_margins[: len(t) + 1]]))
     if return_logits:
         return results, kept_logits
     return results

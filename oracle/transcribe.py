@@ -30,7 +30,7 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
                no_speech_threshold: Optional[float] = 0.6, condition_on_previous_text: bool = True,
                language: Optional[str] = None, task: str = "transcribe", policy: str = "fp32",
                sample_len: Optional[int] = None, fixed_windows: bool = False,
-               max_tail_rounds: int = 8):
+               max_tail_rounds: int = 8, decode_fn=None):
     """Returns {"text", "segments", "language"}.
 
     `fixed_windows=True` is the batched-mode contract of the product (not a mode of the
@@ -38,6 +38,9 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
     would re-seek (tokens left after the last closed timestamp pair) the leftover text becomes a segment ending at
     the window end; if there is no leftover text the uncovered tail [last timestamp, window end) is decoded as a
     window of its own before the next planned window (at most `max_tail_rounds` times per planned window).
+
+    `decode_fn(seek, segment_size, segment_mel, prompt_tokens, temperature) -> DecodingResult` replaces the model for
+    one window (tests replay the tokens another implementation decoded, to check the control flow around them).
     """
     ids = TokenIds(dims.n_vocab)
     mel = A.log_mel_spectrogram(audio, dims.n_mels, padding=A.N_SAMPLES)
@@ -55,11 +58,14 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
     prompt_reset_since = 0
     seek = 0
 
-    def decode_with_fallback(segment):
+    def decode_with_fallback(segment, seek, segment_size):
         result = None
         for t in temps:
-            result = D.decode(w, dims, segment, language=language, task=task, temperature=float(t),
-                              prompt=all_tokens[prompt_reset_since:], policy=policy, sample_len=sample_len)[0]
+            if decode_fn is not None:
+                result = decode_fn(seek, segment_size, segment, all_tokens[prompt_reset_since:], float(t))
+            else:
+                result = D.decode(w, dims, segment, language=language, task=task, temperature=float(t),
+                                  prompt=all_tokens[prompt_reset_since:], policy=policy, sample_len=sample_len)[0]
             needs_fallback = False
             if compression_ratio_threshold is not None and result.compression_ratio > compression_ratio_threshold:
                 needs_fallback = True
@@ -90,7 +96,7 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
             segment_size = window_end - seek
         segment_duration = segment_size * HOP / SR
         segment = torch.from_numpy(_pad_or_trim_frames(mel[seek: seek + segment_size]))[None]
-        result = decode_with_fallback(segment)
+        result = decode_with_fallback(segment, seek, segment_size)
         tokens = np.array(result.tokens, dtype=np.int64)
 
         if no_speech_threshold is not None:

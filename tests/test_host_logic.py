@@ -316,3 +316,50 @@ def test_word_distribution_matches_oracle():
     bad = {"words": [{"word": " uh", "start": 0.0, "end": 0.02, "probability": 0.05}] * 4}
     assert not _is_segment_anomaly(good) and _is_segment_anomaly(bad) and not _is_segment_anomaly(None)
     assert _next_words_segment([{"words": []}, good]) is good and _next_words_segment([{"words": []}]) is None
+
+
+def test_subtitle_word_options(tmp_path):
+    """--highlight-words / --max-line-width / --max-line-count / --max-words-per-line act on the srt / vtt cues
+    (they were parsed and ignored in r01); without word timings they are rejected, not dropped."""
+    from whisper_mlx_b200.writers import get_writer
+
+    def seg(i, t0, words):
+        ws, t = [], t0
+        for w in words:
+            ws.append({"word": w, "start": round(t, 2), "end": round(t + 0.4, 2), "probability": 0.9})
+            t += 0.5
+        return {"id": i, "start": t0, "end": round(t, 2), "text": "".join(words), "words": ws}
+
+    result = {"text": "", "language": "en", "segments": [seg(0, 0.0, [" The", " quick", " brown", " fox", " jumps"]),
+                                                         seg(1, 10.0, [" over", " the", " lazy", " dog"])]}
+    w = get_writer("srt", str(tmp_path))
+
+    def cues(**kw):
+        w(result, "o", **kw)
+        blocks = open(tmp_path / "o.srt").read().strip().split("\n\n")
+        return [b.split("\n", 2)[1:] for b in blocks]
+
+    plain = cues()
+    assert [c[1] for c in plain] == ["The quick brown fox jumps", "over the lazy dog"]
+    assert plain[0][0] == "00:00:00,000 --> 00:00:02,400"  # first word start --> last word end
+    wrapped = cues(max_line_width=12)
+    assert [c[1] for c in wrapped] == ["The quick\nbrown fox\njumps", "over the\nlazy dog"]  # lines wrap, cues stay segments
+    counted = cues(max_line_width=12, max_line_count=2)
+    assert [c[1] for c in counted] == ["The quick\nbrown fox", "jumps", "over the\nlazy dog"]  # 3 s pause also closes a cue
+    assert counted[1][0] == "00:00:02,000 --> 00:00:02,400"
+    per = cues(max_words_per_line=2)
+    assert [c[1] for c in per] == ["The quick", "brown fox", "jumps", "over the", "lazy dog"]
+    hl = cues(highlight_words=True)
+    assert hl[0] == ["00:00:00,000 --> 00:00:00,400", "<u>The</u> quick brown fox jumps"]
+    assert hl[1] == ["00:00:00,400 --> 00:00:00,500", "The quick brown fox jumps"]  # the gap between two words
+    assert hl[2][1] == "The <u>quick</u> brown fox jumps"
+    # vtt goes through the same iterator
+    get_writer("vtt", str(tmp_path))(result, "o", max_words_per_line=3)
+    assert "The quick brown\n" in open(tmp_path / "o.vtt").read()
+    no_words = {"segments": [{"id": 0, "start": 0.0, "end": 1.0, "text": " hi"}]}
+    with pytest.raises(ValueError, match="word_timestamps=True"):
+        w(no_words, "o", highlight_words=True)
+    w(no_words, "o")
+    # txt / tsv / json ignore the cue options (the CLI passes them to every writer)
+    get_writer("all", str(tmp_path))(result, "all", max_line_width=12, max_line_count=None, highlight_words=False, max_words_per_line=None)
+    assert open(tmp_path / "all.txt").read() == "The quick brown fox jumps\nover the lazy dog\n"

@@ -57,6 +57,7 @@ def model():
         res = OD.decode(w, dims, mel, language="en", sample_len=24, policy=pol, audio_features=xa)[0]
         d[f"greedy_{pol}"] = np.array(res.tokens)
         d[f"greedy_meta_{pol}"] = np.array([res.avg_logprob, res.no_speech_prob])
+        d[f"greedy_margins_{pol}"] = np.array(res.margins, dtype=np.float32)  # top-1 / top-2 gap at every sampled token
     np.savez_compressed(os.path.join(OUT, "model_micro.npz"), **d)
 
 
@@ -67,10 +68,18 @@ def transcribe():
     audio = synth.long_audio(75.0, 3)
     out = {}
     for mode, fixed in (("exact", False), ("fixed", True)):
+        windows = []
+
+        def decode_fn(seek, size, segment, prompt, temperature):
+            res = OD.decode(w, dims, segment, language="en", temperature=temperature, prompt=prompt, policy="bf16", sample_len=24)[0]
+            windows.append({"seek": int(seek), "size": int(size), "tokens": res.tokens, "margins": [round(x, 5) for x in res.margins]})
+            return res
+
         r = OT.transcribe(w, dims, audio, temperature=0.0, condition_on_previous_text=False, language="en", sample_len=24,
-                          policy="bf16", fixed_windows=fixed)
+                          policy="bf16", fixed_windows=fixed, decode_fn=decode_fn)
         out[mode] = {"language": r["language"], "text": r["text"],
-                     "segments": [{k: s[k] for k in ("id", "seek", "start", "end", "tokens", "text")} for s in r["segments"]]}
+                     "segments": [{k: s[k] for k in ("id", "seek", "start", "end", "tokens", "text")} for s in r["segments"]],
+                     "windows": windows}  # decoding order, with the top-1 / top-2 gap of every sampled token
     r = OT.transcribe(w, dims, audio[: 16000 * 31], temperature=0.0, condition_on_previous_text=False, sample_len=8)
     out["language_detect"] = r["language"]
     with open(os.path.join(OUT, "transcribe_micro.json"), "w") as f:

@@ -210,6 +210,7 @@ def transcribe(
     rank: int = 0,
     world_size: int = 1,
     max_tail_rounds: int = 8,
+    window_trace: Optional[list] = None,
     _backend=None,
     **decode_options,
 ):
@@ -222,7 +223,8 @@ def transcribe(
     `world_size` (batched mode, one process per GPU with torch.distributed initialised) make this process
     decode only its block of windows and gather the per-window segments on the host, so every rank returns
     the full result; `max_tail_rounds` bounds the follow-up batches that decode uncovered window tails
-    (0: never re-decode a tail).  `_backend` (tests only) replaces the device side -- log-mel, encoder and
+    (0: never re-decode a tail); `window_trace`, a list, receives one dict per decoded window (seek, size, the
+    DecodingResult fields) in decoding order -- diagnostics / parity tests.  `_backend` (tests only) replaces the device side -- log-mel, encoder and
     decoder -- with a stand-in so that the control flow can be exercised on a CPU.
     """
     if word_timestamps and decode_options.get("task", "transcribe") == "translate" and verbose:
@@ -332,6 +334,12 @@ def transcribe(
                 break
         return results
 
+    def trace(seek: int, size: int, res: DecodingResult) -> None:
+        if window_trace is not None:
+            window_trace.append(dict(seek=seek, size=size, tokens=list(res.tokens), avg_logprob=res.avg_logprob,
+                                     no_speech_prob=res.no_speech_prob, temperature=res.temperature,
+                                     compression_ratio=res.compression_ratio, text=res.text))
+
     input_stride = N_FRAMES // model.dims.n_audio_ctx  # mel frames per output token: 2
     time_precision = input_stride * HOP_LENGTH / SAMPLE_RATE  # time per output token: 0.02 (seconds)
     all_tokens: List[int] = []
@@ -382,6 +390,7 @@ def transcribe(
                 features = features_for([c[1] for c in chunk], [c[2] for c in chunk])
                 results = decode_with_fallback(features, [])
                 for (i, seek, size), res in zip(chunk, results):
+                    trace(seek, size, res)
                     if should_skip(res):
                         continue
                     tokens = np.array(res.tokens, dtype=np.int64)
@@ -412,6 +421,7 @@ def transcribe(
             features = features_for([seek], [segment_size])
             result = decode_with_fallback(features, all_tokens[prompt_reset_since:])[0]
             tokens = np.array(result.tokens, dtype=np.int64)
+            trace(seek, segment_size, result)
             if should_skip(result):
                 seek += segment_size  # fast-forward to the next segment boundary
                 continue
