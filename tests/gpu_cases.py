@@ -597,7 +597,7 @@ LOGIT_TOL_BF16 = 4e-2   # vs the 16-bit-storage-policy oracle, logits of std ~1 
 
 
 def _check_greedy_trajectory(w, dims, xa_ref, product_logits, sampled, n_steps, language="en", logit_tol=LOGIT_TOL_BF16,
-                             avg_logprob=None):
+                             avg_logprob=None, greedy=True):
     """xa_ref (1500, d) f32 oracle-side encoder states of ONE window; `sampled`: the tokens the CUDA path produced
     (EOT-trimmed); product_logits: callable(tokens (1, n) long) -> (n, V) f32 teacher-forced logits of the CUDA path.
     Returns {"err", "near_ties", "min_margin_at_tie"}; raises AssertionError when a token is not explained by rounding."""
@@ -625,7 +625,7 @@ def _check_greedy_trajectory(w, dims, xa_ref, product_logits, sampled, n_steps, 
         best = float(row.max())
         assert np.isfinite(row[0, choice]), (j, choice, "the CUDA path sampled a token the rules forbid")
         gap = best - float(row[0, choice])
-        assert gap <= thr, (j, choice, int(row.argmax()), gap, thr, "token differs beyond rounding")
+        assert gap <= thr or not greedy, (j, choice, int(row.argmax()), gap, thr, "token differs beyond rounding")
         if int(row.argmax()) != choice:
             near += 1
             worst = gap if worst is None else max(worst, gap)

@@ -40,8 +40,54 @@ def test_cli_with_the_reference_flags(micro_dir, tmp_path, monkeypatch):
           "--hallucination-silence-threshold", "1", "--verbose", "False", "--temperature-increment-on-fallback", "None",
           "--language", "en"])
     lines = open(tmp_path / "out.txt").read().splitlines()
-    ref = transcribe(x, model=load_model(micro_dir), condition_on_previous_text=False, temperature=0.0, language="en")
+    trace = []
+    m = load_model(micro_dir)
+    ref = transcribe(x, model=m, condition_on_previous_text=False, temperature=0.0, language="en", window_trace=trace)
     assert lines == [s["text"].strip() for s in ref["segments"]] and len(lines) >= 1
+    # ... and that transcript is the reference control flow on tokens that follow the oracle model (not just self-equal)
+    from oracle import model as OM
+    from tests.gpu_cases import _replay_and_validate
+
+    cfg, w = synth.load_weights_f32(micro_dir)
+    kw = dict(temperature=0.0, condition_on_previous_text=False, language="en")
+    n_seg, n_win, near = _replay_and_validate("cli", False, ref, trace, w, OM.ModelDimensions(**cfg), x, m, kw, 224)
+    assert n_seg == len(lines)
+
+
+def test_cli_renders_text_with_the_vocabulary_in_the_model_directory(micro_dir, tmp_path, monkeypatch):
+    """`multilingual.tiktoken` next to the weights: the CLI's text goes through the tiktoken branch end to end (no
+    surrogate allowed), and equals the BPE decoding of the segment tokens."""
+    import shutil
+
+    from tools import synth_vocab
+    from whisper_mlx_b200 import transcribe
+    from whisper_mlx_b200.cli import main
+    from whisper_mlx_b200.load_models import load_model
+    from whisper_mlx_b200.tokenizer import get_tokenizer
+
+    mdir = str(tmp_path / "model")
+    shutil.copytree(micro_dir, mdir)
+    synth_vocab.write_vocab(mdir, "multilingual")
+    monkeypatch.delenv("B200W_ALLOW_SURROGATE", raising=False)
+    wav = str(tmp_path / "in.wav")
+    x = _write_wav(wav, synth.long_audio(35.0, 9))
+    monkeypatch.chdir(tmp_path)
+    main([wav, "-f", "txt", "--output-name", "out", "--model", mdir, "--condition-on-previous-text", "False",
+          "--verbose", "False", "--temperature-increment-on-fallback", "None", "--language", "en"])
+    lines = open(tmp_path / "out.txt").read().splitlines()
+    r = transcribe(x, model=load_model(mdir), condition_on_previous_text=False, temperature=0.0, language="en")
+    tk = get_tokenizer(True, num_languages=99, language="en", task="transcribe", vocab_dir=mdir)
+    assert tk.encoding.has_vocab and len(lines) == len(r["segments"]) >= 1
+    for line, seg in zip(lines, r["segments"]):
+        assert line == tk.decode([t for t in seg["tokens"] if t < tk.eot]).strip()
+    # without the vocabulary (and without the test override) the CLI reports the file instead of writing made-up text
+    os.remove(os.path.join(mdir, "multilingual.tiktoken"))
+    os.remove(tmp_path / "out.txt")
+    from whisper_mlx_b200.transcribe import ModelHolder
+
+    ModelHolder.model = None
+    main([wav, "-f", "txt", "--output-name", "out", "--model", mdir, "--verbose", "False", "--language", "en"])
+    assert not os.path.exists(tmp_path / "out.txt")
 
 
 def test_npz_and_fp16_weights_load_identically(micro_dir, tmp_path):
@@ -85,6 +131,53 @@ def test_sampling_and_best_of(micro_dir):
     # near-zero temperature sampling reproduces greedy decoding
     cold = DecodingTask(m, DecodingOptions(language="en", sample_len=16, temperature=1e-4, best_of=1, seed=3)).run_features(xa)
     assert [r.tokens for r in cold] == [r.tokens for r in greedy]
+
+
+def test_sampling_follows_the_oracle_distribution(micro_dir):
+    """temperature 1 on the device against the oracle's categorical: 512 first-token samples of one window match
+    softmax(filtered logits) within 5 sigma per token, every sampled token is one the rules allow, and the reported
+    avg_logprob is the oracle's sum of log-probabilities of the sampled tokens."""
+    from oracle import decoding as OD, model as OM
+    from oracle.tokens import TokenIds
+    from tests.gpu_cases import _check_greedy_trajectory, _product_logits_fn
+    from whisper_mlx_b200.decoding import DecodeSession, DecodingOptions, DecodingTask
+    from whisper_mlx_b200.load_models import load_model
+
+    m = load_model(micro_dir)
+    cfg, w = synth.load_weights_f32(micro_dir)
+    dims = OM.ModelDimensions(**cfg)
+    ids = TokenIds(dims.n_vocab)
+    g = torch.Generator().manual_seed(5)
+    xa = torch.randn(1, 1500, 128, generator=g).bfloat16()
+    n = 512
+    task = DecodingTask(m, DecodingOptions(language="en", sample_len=8, temperature=1.0, best_of=n, seed=11))
+    sess = DecodeSession(m, xa.cuda(), n, max_tokens=16)
+    n0 = len(task.initial_tokens)
+    sess.set_tokens(torch.tensor(task.initial_tokens, dtype=torch.int32).repeat(n, 1))
+    sess.set_filter(task._filter_params(sess), task._get_suppress_tokens())
+    sess.prompt_step(n0, task.sot_index)
+    torch.cuda.synchronize()
+    first = sess.tokens[:, n0].cpu().numpy()
+    toks = torch.tensor([list(task.initial_tokens)], dtype=torch.long)
+    ref, _ = OM.decoder_forward(w, dims, toks, xa.float(), policy="bf16")
+    row = ref[0, -1:].float().numpy().copy()
+    OD.filter_logits(row, toks.numpy(), n0, ids, ids.suppress_set())
+    p = torch.softmax(torch.from_numpy(row[0]), -1).numpy()
+    assert np.all(p[first] > 0), "a forbidden token was sampled"
+    counts = np.bincount(first, minlength=dims.n_vocab)
+    checked = 0
+    for t in np.argsort(-p)[:12]:
+        if p[t] < 0.02:
+            break
+        sigma = np.sqrt(n * p[t] * (1 - p[t]))
+        assert abs(counts[t] - n * p[t]) <= 5 * sigma + 1, (int(t), int(counts[t]), n * p[t])
+        checked += 1
+    assert checked >= 3 and len(set(first.tolist())) >= 5
+    # whole sampled sequences: allowed tokens + log-probability bookkeeping (best_of picks by mean log-probability)
+    res = DecodingTask(m, DecodingOptions(language="en", sample_len=10, temperature=0.7, best_of=3, seed=4)).run_features(xa.cuda())[0]
+    chk = _check_greedy_trajectory(w, dims, xa[0].float(), _product_logits_fn(m, xa.cuda()), res.tokens, 10,
+                                   avg_logprob=res.avg_logprob, greedy=False)
+    assert chk["n"] >= 1
 
 
 def test_temperature_fallback_in_transcribe(micro_dir):
@@ -174,6 +267,30 @@ def test_mlx_quantised_checkpoint_loads(micro_dir, tmp_path):
     assert torch.equal(mq.embed_audio(mel), md.embed_audio(mel))
 
 
+@pytest.mark.parametrize("fmt,quant", [("npz", None), ("safetensors", dict(group_size=64, bits=4))])
+def test_checkpoint_written_from_the_hf_side(tmp_path, built_lib, fmt, quant):
+    """The loader + engine on an `mlx-community/whisper-*-mlx`-shaped directory produced from a transformers model by the
+    published HF -> MLX conversion rules (tests/hf_bridge.py), i.e. NOT by this repo's own writer: logits must equal the
+    transformers forward pass (fp32) within the bf16 tolerance (4-bit: within the quantisation error, measured on
+    the oracle: see tests/test_assets.py)."""
+    from oracle import audio as OA
+    from tests.test_assets import _hf_logits, _hf_model, write_mlx_checkpoint
+    from whisper_mlx_b200.load_models import load_model
+
+    hf = _hf_model()
+    m = load_model(write_mlx_checkpoint(str(tmp_path / "ckpt"), hf, fmt, quant))
+    assert m.alignment_heads.tolist() == [[1, 0], [1, 1]]
+    mel = torch.from_numpy(OA.log_mel_spectrogram(synth.make_audio("speech", 480000, 5), 80))[None]
+    tokens = torch.tensor([[50258, 50259, 50359, 50364, 400, 500, 50400]])
+    ref = _hf_logits(hf, mel, tokens)
+    got = m.logits(tokens, m.embed_audio(mel)).cpu()
+    err = (got - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item() / 10)
+    assert err <= (8e-2 if quant is None else 0.6) * scale, (fmt, quant, err)
+    if quant is None:
+        assert bool((got.argmax(-1) == ref.argmax(-1)).float().mean() >= 0.7)
+
+
 def _dequant_like(words, scales, biases):
     from whisper_mlx_b200.load_models import dequantize
 
@@ -238,6 +355,17 @@ def test_decode_chain_is_bit_identical_to_separate_launches():
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(repo, "tools", "ab_chain.py"), "small", "64", "12"], capture_output=True,
                          text=True, timeout=600, cwd=repo)
+    assert out.returncode == 0 and "IDENTICAL" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
+def test_decode_chain_bit_identical_at_the_headline_shape():
+    """The same A/B at BASELINE config 4's own shape: large-v3, 120 sequences, 24 graph-replayed steps."""
+    import subprocess
+    import sys
+
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(repo, "tools", "ab_chain.py"), "large-v3", "120", "24"], capture_output=True,
+                         text=True, timeout=900, cwd=repo)
     assert out.returncode == 0 and "IDENTICAL" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
 
 
