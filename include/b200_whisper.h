@@ -71,6 +71,14 @@ int b200w_logmel(const float* pcm, int n_audio, long long audio_stride, long lon
  * b200w_logmel on the converted floats.  audio_stride in samples. */
 int b200w_logmel_pcm16(const int16_t* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
                        int n_mels, const b200w_logmel_tables* tables, float* out_unclamped, float* gmax, void* stream);
+/* The whole of UPSTREAM log_mel_spectrogram in ONE pass over HBM: `out` receives the normalised values
+ * (max(log10 mel, max_a - 8) + 4) / 4.  pcm is f32 (pcm_is_int16 == 0) or s16le.  The clamp needs the maximum over
+ * the whole signal, so the kernel normalises a tile two scheduling rounds after it stored it, once every tile of the
+ * signal has been counted in done_tiles (n_audio ints, scratch; zeroed by the call) -- the rows are still in L2.
+ * Launched cooperatively (its CTAs wait for one another).  gmax[a] receives the maximum as in b200w_logmel. */
+int b200w_logmel_normalized(const void* pcm, int pcm_is_int16, int n_audio, long long audio_stride, long long n_valid,
+                            long long n_total, int n_mels, const b200w_logmel_tables* tables, float* out, float* gmax,
+                            int* done_tiles, void* stream);
 /* In place: x <- (max(x, gmax[a] - 8) + 4) / 4 for the per_audio values of each signal. */
 int b200w_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, void* stream);
 /* Window gather fused with the clamp/scale and the bf16 cast that feeds the conv stem.  Replaces

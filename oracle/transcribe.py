@@ -137,7 +137,7 @@ def transcribe(w, dims: M.ModelDimensions, audio: np.ndarray, *,
                     current.append(new_segment(time_offset + start_pos * time_precision, time_offset + segment_duration,
                                                trailing, result))
                     seek += segment_size
-                elif advance > 0 and tail_rounds < max_tail_rounds:
+                elif 0 < advance < segment_size and tail_rounds < max_tail_rounds:
                     tail_rounds += 1
                     seek += advance  # the tail [seek, window_end) is decoded next
                 else:

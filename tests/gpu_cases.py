@@ -744,7 +744,7 @@ def _config_decode_case(name: str, batch: int, n_steps: int):
                     audio_features=base.float())
     for i in range(4):
         chk = _check_greedy_trajectory(w32, dims, base[i].float(), _product_logits_fn(m, xa[i: i + 1]), got[i].tokens,
-                                       n_steps, logit_tol=8e-2 if dims.n_text_layer >= 32 else LOGIT_TOL_BF16,
+                                       n_steps, logit_tol=8e-2,  # unit-variance random encoder states, up to 32 layers
                                        avg_logprob=got[i].avg_logprob)
         out[f"w{i}"] = chk
         assert abs(got[i].no_speech_prob - ref[i].no_speech_prob) <= 0.05 * max(ref[i].no_speech_prob, 1e-6) + 1e-7

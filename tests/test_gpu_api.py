@@ -74,12 +74,11 @@ def test_cli_renders_text_with_the_vocabulary_in_the_model_directory(micro_dir, 
     monkeypatch.chdir(tmp_path)
     main([wav, "-f", "txt", "--output-name", "out", "--model", mdir, "--condition-on-previous-text", "False",
           "--verbose", "False", "--temperature-increment-on-fallback", "None", "--language", "en"])
-    lines = open(tmp_path / "out.txt").read().splitlines()
+    written = open(tmp_path / "out.txt", newline="").read()  # (random tokens decode to bytes that include line breaks)
     r = transcribe(x, model=load_model(mdir), condition_on_previous_text=False, temperature=0.0, language="en")
     tk = get_tokenizer(True, num_languages=99, language="en", task="transcribe", vocab_dir=mdir)
-    assert tk.encoding.has_vocab and len(lines) == len(r["segments"]) >= 1
-    for line, seg in zip(lines, r["segments"]):
-        assert line == tk.decode([t for t in seg["tokens"] if t < tk.eot]).strip()
+    assert tk.encoding.has_vocab and len(r["segments"]) >= 1
+    assert written == "".join(tk.decode([t for t in seg["tokens"] if t < tk.eot]).strip() + "\n" for seg in r["segments"])
     # without the vocabulary (and without the test override) the CLI reports the file instead of writing made-up text
     os.remove(os.path.join(mdir, "multilingual.tiktoken"))
     os.remove(tmp_path / "out.txt")

@@ -87,7 +87,7 @@ def _oracle_segments(tokens, seek, size, fixed):
             if any(t < ids.eot for t in trailing):
                 start = trailing[0] - ids.timestamp_begin if trailing[0] >= ids.timestamp_begin else adv // 2
                 segs.append((t0 + start * 0.02, t0 + size * 0.01, trailing))
-            elif adv > 0:
+            elif 0 < adv < size:
                 tail = (seek + adv, size - adv)
     else:
         dur = size * 160 / 16000
@@ -115,21 +115,23 @@ def test_segmentation_matches_oracle(fixed):
         [tb, 10, 11, 12],                                                   # no closing timestamp
         [tb + 20, 7, tb + 60, tb + 60, 8, tb + 90],                         # pair then single ending
         [tb, tb],                                                           # empty pair at 0: no progress possible
+        [tb, 10, tb + 1400, tb + 1400, 11],                                 # (1500-frame window) timestamps past the window end
+        [tb, 10, tb + 1400, tb + 1400],                                     # ... and nothing after them: no tail to decode
         [10, 11, 12],
         [],
     ]
-    for s in streams:
+    for s, size in [(s, size) for s in streams for size in (3000, 1500)]:
         res = DecodingResult(audio_features=None, language="en", tokens=s, avg_logprob=-0.5, no_speech_prob=0.0, temperature=0.0,
                              compression_ratio=1.0)
         toks = np.array(s, dtype=np.int64)
         if fixed:
-            segs, got2 = _segments_fixed_window(toks, 3000, 3000, res, tk, 2, 0.02)
+            segs, got2 = _segments_fixed_window(toks, 3000, size, res, tk, 2, 0.02)
         else:
-            segs, got2, _, _ = _segments_for_window(toks, 3000, 3000, res, tk, 2, 0.02)
+            segs, got2, _, _ = _segments_for_window(toks, 3000, size, res, tk, 2, 0.02)
         _clear_empty_segments(segs, with_words=False)
-        ref, ref2 = _oracle_segments(s, 3000, 3000, fixed)
-        assert got2 == ref2, (s, got2, ref2)
-        assert len(segs) == len(ref)
+        ref, ref2 = _oracle_segments(s, 3000, size, fixed)
+        assert got2 == ref2, (s, size, got2, ref2)
+        assert len(segs) == len(ref), (s, size)
         for g, (st, en, toks_ref) in zip(segs, ref):
             assert abs(g["start"] - st) < 1e-9 and abs(g["end"] - en) < 1e-9
             if g["start"] != g["end"] and g["text"].strip():

@@ -74,6 +74,7 @@ SIGNATURES = {
     "b200w_profile_end": (i32, [C.c_char_p, sz]),
     "b200w_logmel": (i32, [vp, i32, i64, i64, i64, i32, C.POINTER(LogmelTables), vp, vp, vp]),
     "b200w_logmel_pcm16": (i32, [vp, i32, i64, i64, i64, i32, C.POINTER(LogmelTables), vp, vp, vp]),
+    "b200w_logmel_normalized": (i32, [vp, i32, i32, i64, i64, i64, i32, C.POINTER(LogmelTables), vp, vp, vp, vp]),
     "b200w_logmel_finalize": (i32, [vp, vp, i32, i64, vp]),
     "b200w_mel_windows": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp]),
     "b200w_gemm_bf16": (i32, [vp, i64, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp]),

@@ -182,12 +182,7 @@ def _to_device_audio(audio, device=None) -> torch.Tensor:
     return audio.to(torch.int16 if audio.dtype == torch.int16 else torch.float32).contiguous()
 
 
-def log_mel_unclamped(audio: torch.Tensor, n_mels: int = 80, padding: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Run K1 on `audio` ((n,) or (n_audio, n) f32 or int16-PCM CUDA).  Returns (log10 mel before the clamp, per-audio max).
-
-    The clamp / scale is applied by `log_mel_spectrogram` (K1b in place) or fused into the bf16 window
-    gather that feeds the encoder (`Whisper.mel_windows`).
-    """
+def _run_logmel(audio: torch.Tensor, n_mels: int, padding: int, normalized: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     x = audio if audio.ndim == 2 else audio[None]
     _lib.require_cuda(x, "audio")
@@ -202,10 +197,24 @@ def log_mel_unclamped(audio: torch.Tensor, n_mels: int = 80, padding: int = 0) -
     out = torch.empty((n_audio, n_frames, n_mels), dtype=torch.float32, device=x.device)
     gmax = torch.empty((n_audio,), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        fn = lib.b200w_logmel_pcm16 if x.dtype == torch.int16 else lib.b200w_logmel
-        _lib.check(fn(_lib.ptr(x), n_audio, x.stride(0), n_valid, n_total, n_mels, tb.struct, _lib.ptr(out), _lib.ptr(gmax),
-                      _lib.stream()))
+        if normalized:
+            done = torch.empty((n_audio,), dtype=torch.int32, device=x.device)
+            _lib.check(lib.b200w_logmel_normalized(_lib.ptr(x), int(x.dtype == torch.int16), n_audio, x.stride(0), n_valid, n_total,
+                                                   n_mels, tb.struct, _lib.ptr(out), _lib.ptr(gmax), _lib.ptr(done), _lib.stream()))
+        else:
+            fn = lib.b200w_logmel_pcm16 if x.dtype == torch.int16 else lib.b200w_logmel
+            _lib.check(fn(_lib.ptr(x), n_audio, x.stride(0), n_valid, n_total, n_mels, tb.struct, _lib.ptr(out), _lib.ptr(gmax),
+                          _lib.stream()))
     return out, gmax
+
+
+def log_mel_unclamped(audio: torch.Tensor, n_mels: int = 80, padding: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Run K1 on `audio` ((n,) or (n_audio, n) f32 or int16-PCM CUDA).  Returns (log10 mel before the clamp, per-audio max).
+
+    The clamp / scale is fused into the bf16 window gather that feeds the encoder (`Whisper.mel_windows`);
+    `log_mel_spectrogram` runs the kernel with the normalisation fused instead.
+    """
+    return _run_logmel(audio, n_mels, padding, normalized=False)
 
 
 def log_mel_spectrogram(audio: Union[str, np.ndarray, torch.Tensor], n_mels: int = 80, padding: int = 0,
@@ -219,9 +228,12 @@ def log_mel_spectrogram(audio: Union[str, np.ndarray, torch.Tensor], n_mels: int
     """
     x = _to_device_audio(audio, device)
     batched = x.ndim == 2
-    out, gmax = log_mel_unclamped(x, n_mels, padding)
-    lib = _lib.load()
-    with torch.cuda.device(out.device):
-        _lib.check(lib.b200w_logmel_finalize(_lib.ptr(out), _lib.ptr(gmax), out.shape[0], out.shape[1] * out.shape[2],
-                                             _lib.stream()))
+    if os.environ.get("B200W_LOGMEL_TWO_PASS") == "1":  # A/B: the r01 form, clamp as a second pass over the result
+        out, gmax = log_mel_unclamped(x, n_mels, padding)
+        lib = _lib.load()
+        with torch.cuda.device(out.device):
+            _lib.check(lib.b200w_logmel_finalize(_lib.ptr(out), _lib.ptr(gmax), out.shape[0], out.shape[1] * out.shape[2],
+                                                 _lib.stream()))
+    else:
+        out, _ = _run_logmel(x, n_mels, padding, normalized=True)
     return out if batched else out[0]

@@ -396,6 +396,17 @@ int b200w_logmel_pcm16(const int16_t* pcm, int n_audio, long long audio_stride, 
                              (cudaStream_t)stream);
 }
 
+int b200w_logmel_normalized(const void* pcm, int pcm_is_int16, int n_audio, long long audio_stride, long long n_valid,
+                            long long n_total, int n_mels, const b200w_logmel_tables* t, float* out, float* gmax,
+                            int* done_tiles, void* stream) {
+  B200W_CHECK_ARG(pcm && t && out && gmax && done_tiles, "logmel_normalized: null pointer");
+  if (pcm_is_int16)
+    return launch_logmel_pcm16(static_cast<const int16_t*>(pcm), n_audio, audio_stride, n_valid, n_total, n_mels, t->hann,
+                               t->tw400, out, gmax, (cudaStream_t)stream, done_tiles);
+  return launch_logmel(static_cast<const float*>(pcm), n_audio, audio_stride, n_valid, n_total, n_mels, t->hann, t->tw400, out,
+                       gmax, (cudaStream_t)stream, done_tiles);
+}
+
 int b200w_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, void* stream) {
   B200W_CHECK_ARG(x && gmax && n_audio > 0 && per_audio > 0, "logmel_finalize: bad arguments");
   return launch_logmel_finalize(x, gmax, n_audio, per_audio, (cudaStream_t)stream);

@@ -16,12 +16,14 @@ int init_attention();
 int init_logmel();
 
 // ---------------------------------------------------------------------------------------- K1 log-mel
+// done_tiles == null: `out` receives log10(mel) before the clamp; else (n_audio ints) the clamp / scale is fused and `out`
+// receives the normalised log-mel (cooperative launch)
 int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
-                  int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
-                  cudaStream_t stream);
+                  int n_mels, const float* hann, const float* tw400, float* out, float* gmax,
+                  cudaStream_t stream, int* done_tiles = nullptr);
 int launch_logmel_pcm16(const int16_t* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
-                  int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
-                  cudaStream_t stream);
+                  int n_mels, const float* hann, const float* tw400, float* out, float* gmax,
+                  cudaStream_t stream, int* done_tiles = nullptr);
 int launch_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, cudaStream_t stream);
 int launch_mel_windows(const float* mel, const float* gmax, const long long* row0, const int* size, const int* gidx,
                        int n_windows, int n_mels, __nv_bfloat16* dst, cudaStream_t stream);

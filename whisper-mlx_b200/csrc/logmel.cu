@@ -45,7 +45,7 @@ __device__ __forceinline__ void mel_for_warp(const float* __restrict__ pw, float
     float acc = 0.0f;
 #pragma unroll
     for (int j = 0; j < Bank::kMaxCnt; ++j)
-      if (j < Bank::cnt(m)) acc = fmaf(Bank::w(Bank::off(m) + j), pw[Bank::lo(m) + j], acc);
+      if (j < Bank::cnt(m)) acc = fmaf(0.25f * Bank::w(Bank::off(m) + j), pw[Bank::lo(m) + j], acc);  // (the /4 of the split)
     const float v = 0.30102999566398120f * __log2f(fmaxf(acc, 1e-10f));
     so[m] = v;
     vmax = fmaxf(vmax, v);
@@ -71,7 +71,7 @@ template <int NM, typename PcmT>
 __global__ void __launch_bounds__(kLmThreads, 2)
 logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_valid, long long n_total,
               int n_frames, int tiles_per_audio, int n_tiles, LogmelTables tb, float* __restrict__ out,
-              float* __restrict__ gmax) {
+              float* __restrict__ gmax, int* __restrict__ done_tiles) {
   constexpr int n_mels = NM;
   extern __shared__ __align__(16) unsigned char lm_smem[];
   float* buf_cur = reinterpret_cast<float*>(lm_smem);
@@ -117,6 +117,35 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
     cp_async_commit();
   };
 
+  // K1b fused (done_tiles != null; cooperative launch, every CTA resident): the clamp needs the maximum over the WHOLE
+  // audio, so a tile can only be normalised once all tiles of its audio are stored.  A CTA therefore normalises the tile
+  // it produced two rounds earlier -- by then its audio is complete (the wait below practically never spins) and the
+  // 16 KB are still in L2: no second pass over HBM.  done_tiles[a] counts the stored tiles of audio a.
+  auto finalize_tile = [&](int t) {
+    const int a = t / tiles_per_audio;
+    const int tf0 = (t - a * tiles_per_audio) * kFrames;
+    if (tid == 0) {
+      unsigned int spins = 0;
+      while (*reinterpret_cast<volatile int*>(done_tiles + a) < tiles_per_audio) {
+        if (++spins > (1u << 28)) __trap();  // a lost CTA must not hang the GPU
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    const float fl = __ldcg(gmax + a) - 8.0f;
+    const int n = min(kFrames, n_frames - tf0) * NM;  // floats of this tile, contiguous, 16-byte aligned
+    float4* o4 = reinterpret_cast<float4*>(out + ((long long)a * n_frames + tf0) * NM);
+    for (int i = tid; i < n / 4; i += kLmThreads) {
+      float4 v = __ldcg(o4 + i);
+      v.x = (fmaxf(v.x, fl) + 4.0f) * 0.25f;
+      v.y = (fmaxf(v.y, fl) + 4.0f) * 0.25f;
+      v.z = (fmaxf(v.z, fl) + 4.0f) * 0.25f;
+      v.w = (fmaxf(v.w, fl) + 4.0f) * 0.25f;
+      o4[i] = v;
+    }
+  };
+  int pend0 = -1, pend1 = -1;  // this CTA's stored tiles that are not normalised yet (newest, older)
+
   int tile = blockIdx.x;
   if (tile < n_tiles) stage_tile(buf_cur, tile);
   for (; tile < n_tiles; tile += gridDim.x) {
@@ -128,8 +157,9 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
   __syncthreads();  // samples of this tile have landed; the previous tile's staged rows / power are no longer read
 
   // ---- phase 1: 25 column DFT-16 per pair + W400 twiddle ------------------------------------------
-  // thread t < 250 owns column n2 = t % 25 for pairs t / 25 and t / 25 + 10: window and twiddles stay in registers
-  if (tid < 250) {
+  // thread t < 200 owns column n2 = t % 25 for pairs t / 25 and t / 25 + 8 (two each: no warp waits at the barrier for
+  // a straggler with an extra pair); window and twiddles stay in registers
+  if (tid < 200) {
     const int n2 = tid % 25, g = tid / 25;
     float hw[16];
 #pragma unroll
@@ -139,7 +169,7 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
 #pragma unroll
     for (int i = 0; i < 8; ++i) tw[i] = __ldg(twp + i);
 #pragma unroll 1
-    for (int p = g; p < kPairs; p += 10) {
+    for (int p = g; p < kPairs; p += 8) {
       const float* fa = s_samples + (2 * p) * kHop + n2;
       const float* fb = fa + kHop;
       lm::cpx a[16];
@@ -184,8 +214,8 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
       const float ar = a[k2].re + zr, ai = a[k2].im - zi;
       const float br = a[k2].re - zr, bi = a[k2].im + zi;
       if (k1 + 16 * k2 <= 200) {
-        pa[16 * k2] = 0.25f * (ar * ar + ai * ai);
-        pb[16 * k2] = 0.25f * (br * br + bi * bi);
+        pa[16 * k2] = ar * ar + ai * ai;  // 4 |Xa|^2: the factor 1/4 is folded into the mel weights (exact)
+        pb[16 * k2] = br * br + bi * bi;
       }
     }
   }
@@ -212,9 +242,21 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
   __syncthreads();
   const int valid_frames = min(kFrames, n_frames - f0);
   float* o = out + ((long long)audio * n_frames + f0) * n_mels;
-  for (int item = tid; item < valid_frames * n_mels; item += kLmThreads) {
-    const int f = item / n_mels, m = item - f * n_mels;
-    o[item] = s_out[f * kOutStride + m];
+  {
+    // thread -> (column m, first row r0), rows r0, r0 + kRows, ...: immediate offsets, conflict-free LDS, coalesced STG
+    constexpr int kRows = kLmThreads / NM;  // 2 rows per pass (128 mels) or 3 (80 mels; 16 threads idle)
+    const int m = tid % NM, r0 = tid / NM;
+    if (r0 < kRows) {
+      const float* sp = s_out + r0 * kOutStride + m;
+      float* op = o + r0 * NM + m;
+      if (valid_frames == kFrames) {
+#pragma unroll
+        for (int i = 0; i * kRows < kFrames; ++i)
+          if (i * kRows + kRows <= kFrames || r0 + i * kRows < kFrames) op[i * kRows * NM] = sp[i * kRows * kOutStride];
+      } else {
+        for (int r = r0; r < valid_frames; r += kRows) o[r * NM + m] = s_out[r * kOutStride + m];
+      }
+    }
   }
   vmax = warp_max(vmax);
   if (lane == 0) s_red[warp] = vmax;
@@ -224,16 +266,32 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
 #pragma unroll
     for (int i = 1; i < kLmThreads / 32; ++i) m = fmaxf(m, s_red[i]);
     if (m > -INFINITY) atomic_max_float(gmax + audio, m);
+    if (done_tiles != nullptr) {
+      __threadfence();  // rows (made visible to this thread by the barrier above) and the maximum before the count
+      atomicAdd(done_tiles + audio, 1);
+    }
+  }
+  if (done_tiles != nullptr) {
+    if (pend1 >= 0) finalize_tile(pend1);
+    pend1 = pend0;
+    pend0 = tile;
   }
   float* t = buf_cur;
   buf_cur = buf_nxt;
   buf_nxt = t;
   }
+  if (done_tiles != nullptr) {
+    if (pend1 >= 0) finalize_tile(pend1);
+    if (pend0 >= 0) finalize_tile(pend0);
+  }
 }
 
-__global__ void fill_f32_kernel(float* p, float v, int n) {
+__global__ void fill_f32_kernel(float* p, float v, int* counters, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+  if (i < n) {
+    p[i] = v;
+    if (counters != nullptr) counters[i] = 0;
+  }
 }
 
 // K1b (f32 API result): x <- (max(x, gmax[audio] - 8) + 4) / 4, in place.
@@ -304,7 +362,7 @@ int init_logmel() {
 
 template <typename PcmT>
 static int launch_logmel_t(const PcmT* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
-                           int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
+                           int n_mels, const float* hann, const float* tw400, float* out, float* gmax, int* done_tiles,
                            cudaStream_t stream) {
   // the reflect pad works on the zero-extended signal (UPSTREAM pads first): only its total length must exceed the pad
   B200W_CHECK_ARG(n_audio > 0 && n_valid >= 0 && n_total >= n_valid && n_total > kNfft / 2,
@@ -312,24 +370,28 @@ static int launch_logmel_t(const PcmT* pcm, int n_audio, long long audio_stride,
   B200W_CHECK_ARG(n_mels == 80 || n_mels == 128, "logmel: n_mels must be 80 or 128, got %d", n_mels);
   const long long n_frames_ll = n_total / kHop;
   B200W_CHECK_ARG(n_frames_ll > 0 && n_frames_ll < (1ll << 31) / 128, "logmel: frame count out of range");
-  const int n_frames = (int)n_frames_ll;
+  int n_frames = (int)n_frames_ll;
   const size_t smem = logmel_smem_bytes();
   B200W_TRY(init_logmel());
   ProfScope prof_("logmel", stream);
-  fill_f32_kernel<<<ceil_div(n_audio, 256), 256, 0, stream>>>(gmax, -INFINITY, n_audio);
+  fill_f32_kernel<<<ceil_div(n_audio, 256), 256, 0, stream>>>(gmax, -INFINITY, done_tiles, n_audio);
   B200W_LAUNCH_OK();
   LogmelTables tb{hann, reinterpret_cast<const float2*>(tw400)};
-  const int tiles_per_audio = ceil_div(n_frames, kFrames);
+  int tiles_per_audio = ceil_div(n_frames, kFrames);
   const long long n_tiles_ll = (long long)tiles_per_audio * n_audio;
   B200W_CHECK_ARG(n_tiles_ll < (1ll << 31), "logmel: too many tiles");
-  const int n_tiles = (int)n_tiles_ll;
+  int n_tiles = (int)n_tiles_ll;
   const int grid = n_tiles < 2 * device_sm_count() ? n_tiles : 2 * device_sm_count();
-  if (n_mels == 80)
-    logmel_kernel<80, PcmT><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames,
-                                                                tiles_per_audio, n_tiles, tb, out_unclamped, gmax);
-  else
-    logmel_kernel<128, PcmT><<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames,
-                                                                 tiles_per_audio, n_tiles, tb, out_unclamped, gmax);
+  auto kernel = n_mels == 80 ? logmel_kernel<80, PcmT> : logmel_kernel<128, PcmT>;
+  if (done_tiles == nullptr) {
+    kernel<<<grid, kLmThreads, smem, stream>>>(pcm, audio_stride, n_valid, n_total, n_frames, tiles_per_audio, n_tiles, tb, out,
+                                               gmax, done_tiles);
+  } else {
+    // fused normalisation: CTAs wait for one another's tiles, so all of them must be resident -- cooperative launch
+    void* args[] = {(void*)&pcm, (void*)&audio_stride, (void*)&n_valid, (void*)&n_total, (void*)&n_frames,
+                    (void*)&tiles_per_audio, (void*)&n_tiles, (void*)&tb, (void*)&out, (void*)&gmax, (void*)&done_tiles};
+    B200W_CUDA_OK(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(kLmThreads), args, smem, stream));
+  }
   B200W_LAUNCH_OK();
   count_launch(2);
   return kOk;
@@ -337,14 +399,14 @@ static int launch_logmel_t(const PcmT* pcm, int n_audio, long long audio_stride,
 
 int launch_logmel(const float* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
                   int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
-                  cudaStream_t stream) {
-  return launch_logmel_t(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, hann, tw400, out_unclamped, gmax, stream);
+                  cudaStream_t stream, int* done_tiles) {
+  return launch_logmel_t(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, hann, tw400, out_unclamped, gmax, done_tiles, stream);
 }
 
 int launch_logmel_pcm16(const int16_t* pcm, int n_audio, long long audio_stride, long long n_valid, long long n_total,
                         int n_mels, const float* hann, const float* tw400, float* out_unclamped, float* gmax,
-                        cudaStream_t stream) {
-  return launch_logmel_t(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, hann, tw400, out_unclamped, gmax, stream);
+                        cudaStream_t stream, int* done_tiles) {
+  return launch_logmel_t(pcm, n_audio, audio_stride, n_valid, n_total, n_mels, hann, tw400, out_unclamped, gmax, done_tiles, stream);
 }
 
 int launch_logmel_finalize(float* x, const float* gmax, int n_audio, long long per_audio, cudaStream_t stream) {

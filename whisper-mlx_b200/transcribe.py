@@ -171,7 +171,7 @@ def _segments_fixed_window(tokens: np.ndarray, seek: int, segment_size: int, res
     segs, advance, _, trailing = _segments_for_window(tokens, seek, segment_size, result, tokenizer, input_stride,
                                                       time_precision)
     tail = None
-    if advance < segment_size:  # the reference would re-seek to the last closed timestamp
+    if len(trailing) > 0:  # the reference would re-seek to the last closed timestamp (trailing starts with the opening one)
         if any(int(t) < tokenizer.eot for t in trailing):
             # unfinished text: keep it, as a segment from its opening timestamp to the end of the window
             time_offset = float(seek * HOP_LENGTH / SAMPLE_RATE)
@@ -183,7 +183,7 @@ def _segments_fixed_window(tokens: np.ndarray, seek: int, segment_size: int, res
                          "text": tokenizer.decode([t for t in toks if t < tokenizer.eot]), "tokens": toks,
                          "temperature": result.temperature, "avg_logprob": result.avg_logprob,
                          "compression_ratio": result.compression_ratio, "no_speech_prob": result.no_speech_prob})
-        elif advance > 0:
+        elif 0 < advance < segment_size:
             tail = (seek + advance, segment_size - advance)
     return segs, tail
 
