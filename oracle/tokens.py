@@ -71,6 +71,23 @@ def surrogate_piece(token_id: int) -> bytes:
     return bytes(out)
 
 
+def special_name(token_id: int, timestamp_begin: int) -> str:
+    """Name of a special token below the timestamps, as tiktoken renders it (specials follow the 50257
+    ranks in the order eot, sot, languages, translate, transcribe, startoflm, startofprev, nospeech, notimestamps)."""
+    n_lang = timestamp_begin - 50259 - 6
+    names = ["endoftext", "startoftranscript", *LANGUAGE_CODES[:n_lang], "translate", "transcribe", "startoflm", "startofprev",
+             "nospeech", "notimestamps"]
+    return f"<|{names[token_id - 50257]}|>"
+
+
 def decode_text(token_ids, timestamp_begin: int) -> str:
-    """`Tokenizer.decode`: drops ids >= timestamp_begin, joins pieces (surrogate vocabulary)."""
-    return b"".join(surrogate_piece(int(t)) for t in token_ids if int(t) < timestamp_begin).decode("utf-8")
+    """`Tokenizer.decode`: drops ids >= timestamp_begin, joins pieces (surrogate vocabulary for the BPE ranks; special
+    tokens below the timestamps -- a model can sample e.g. a language token -- are rendered by name like tiktoken does)."""
+    out = []
+    for t in token_ids:
+        t = int(t)
+        if t < 50257:
+            out.append(surrogate_piece(t))
+        elif t < timestamp_begin:
+            out.append(special_name(t, timestamp_begin).encode())
+    return b"".join(out).decode("utf-8")

@@ -119,30 +119,45 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
 
   // K1b fused (done_tiles != null; cooperative launch, every CTA resident): the clamp needs the maximum over the WHOLE
   // audio, so a tile can only be normalised once all tiles of its audio are stored.  A CTA therefore normalises the tile
-  // it produced two rounds earlier -- by then its audio is complete (the wait below practically never spins) and the
-  // 16 KB are still in L2: no second pass over HBM.  done_tiles[a] counts the stored tiles of audio a.
-  auto finalize_tile = [&](int t) {
+  // it produced two rounds earlier -- by then its audio is complete (the wait practically never spins) and the 16 KB
+  // are still in L2: no second pass over HBM.  done_tiles[a] counts the stored tiles of audio a.  The work hides in
+  // the tile loop: warp 7 (idle in phase 1) waits for the count and fetches the clamp floor; after phase 3 the rows
+  // stream back into the free part of the FFT work area with cp.async; after the row stores every thread clamps the
+  // chunks it fetched itself and writes them out.
+  __shared__ float s_floor;
+  float* s_back = reinterpret_cast<float*>(s_work) + kFrames * kOutStride;  // behind the staged rows: 16.5 KB .. 33 KB
+  static_assert((kFrames * kOutStride * sizeof(float)) % 16 == 0, "cp.async destination alignment");
+  static_assert(sizeof(float) * (kFrames * kOutStride + kFrames * 128) <= sizeof(lm::cpx) * kPairs * kPairStride, "fits the work area");
+  auto tile_rows = [&](int t, int& n_floats) -> float* {
     const int a = t / tiles_per_audio;
     const int tf0 = (t - a * tiles_per_audio) * kFrames;
-    if (tid == 0) {
-      unsigned int spins = 0;
-      while (*reinterpret_cast<volatile int*>(done_tiles + a) < tiles_per_audio) {
-        if (++spins > (1u << 28)) __trap();  // a lost CTA must not hang the GPU
-      }
-      __threadfence();
+    n_floats = min(kFrames, n_frames - tf0) * NM;  // contiguous, 16-byte aligned
+    return out + ((long long)a * n_frames + tf0) * NM;
+  };
+  auto wait_floor = [&](int t) {  // one thread: the audio of tile t is complete -> its clamp floor
+    const int a = t / tiles_per_audio;
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile int*>(done_tiles + a) < tiles_per_audio) {
+      if (++spins > (1u << 28)) __trap();  // a lost CTA must not hang the GPU
     }
+    __threadfence();
+    s_floor = __ldcg(gmax + a) - 8.0f;
+  };
+  auto clamp4 = [](float4 v, float fl) {
+    v.x = (fmaxf(v.x, fl) + 4.0f) * 0.25f;
+    v.y = (fmaxf(v.y, fl) + 4.0f) * 0.25f;
+    v.z = (fmaxf(v.z, fl) + 4.0f) * 0.25f;
+    v.w = (fmaxf(v.w, fl) + 4.0f) * 0.25f;
+    return v;
+  };
+  auto finalize_tile = [&](int t) {  // unpipelined form, for the tiles left over when the loop ends
+    if (tid == 0) wait_floor(t);
     __syncthreads();
-    const float fl = __ldcg(gmax + a) - 8.0f;
-    const int n = min(kFrames, n_frames - tf0) * NM;  // floats of this tile, contiguous, 16-byte aligned
-    float4* o4 = reinterpret_cast<float4*>(out + ((long long)a * n_frames + tf0) * NM);
-    for (int i = tid; i < n / 4; i += kLmThreads) {
-      float4 v = __ldcg(o4 + i);
-      v.x = (fmaxf(v.x, fl) + 4.0f) * 0.25f;
-      v.y = (fmaxf(v.y, fl) + 4.0f) * 0.25f;
-      v.z = (fmaxf(v.z, fl) + 4.0f) * 0.25f;
-      v.w = (fmaxf(v.w, fl) + 4.0f) * 0.25f;
-      o4[i] = v;
-    }
+    const float fl = s_floor;
+    int n;
+    float4* o4 = reinterpret_cast<float4*>(tile_rows(t, n));
+    for (int i = tid; i < n / 4; i += kLmThreads) o4[i] = clamp4(__ldcg(o4 + i), fl);
+    __syncthreads();  // s_floor is rewritten by the next call
   };
   int pend0 = -1, pend1 = -1;  // this CTA's stored tiles that are not normalised yet (newest, older)
 
@@ -159,6 +174,7 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
   // ---- phase 1: 25 column DFT-16 per pair + W400 twiddle ------------------------------------------
   // thread t < 200 owns column n2 = t % 25 for pairs t / 25 and t / 25 + 8 (two each: no warp waits at the barrier for
   // a straggler with an extra pair); window and twiddles stay in registers
+  if (done_tiles != nullptr && pend1 >= 0 && tid == kLmThreads - 32) wait_floor(pend1);  // (warp 7 has no column work)
   if (tid < 200) {
     const int n2 = tid % 25, g = tid / 25;
     float hw[16];
@@ -221,6 +237,13 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
   }
   __syncthreads();
 
+  if (done_tiles != nullptr && pend1 >= 0) {  // the FFT work area is free behind the staged rows
+    int n;
+    const float* src = tile_rows(pend1, n);
+    for (int i = tid; i < n / 4; i += kLmThreads) cp_async16(s_back + 4 * i, src + 4 * i);
+    cp_async_commit();
+  }
+
   // ---- phase 5: sparse mel with one lane per frame, log10, staged rows, running max ---------------------
   // every lane of a warp walks the same (mel, bin) sequence: no divergence, weights are warp-uniform loads
   float vmax = -INFINITY;
@@ -272,7 +295,13 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
     }
   }
   if (done_tiles != nullptr) {
-    if (pend1 >= 0) finalize_tile(pend1);
+    if (pend1 >= 0) {  // every thread clamps the chunks it fetched itself: only its own copies need to have landed
+      cp_async_wait_all();
+      const float fl = s_floor;  // written in phase 1, barriers since
+      int n;
+      float4* o4 = reinterpret_cast<float4*>(tile_rows(pend1, n));
+      for (int i = tid; i < n / 4; i += kLmThreads) o4[i] = clamp4(*reinterpret_cast<const float4*>(s_back + 4 * i), fl);
+    }
     pend1 = pend0;
     pend0 = tile;
   }
@@ -281,6 +310,7 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
   buf_nxt = t;
   }
   if (done_tiles != nullptr) {
+    __syncthreads();  // s_floor of the last pipelined clamp has been read by everyone
     if (pend1 >= 0) finalize_tile(pend1);
     if (pend0 >= 0) finalize_tile(pend0);
   }
