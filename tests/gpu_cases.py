@@ -797,6 +797,69 @@ def case_config5_turbo_batch256():
     return _config_decode_case("large-v3-turbo", 256, 16)
 
 
+def case_small_batch_step():
+    """K13 (one cooperative launch per single-token step for <= 6 sequences -- the exact sequential mode and its
+    `best_of` fallback) against the large-batch path (K11 chains + attention kernels) and the oracle: teacher-forced
+    logits over a token sequence that crosses a KV page boundary, batches 1 / 2 / 5 / 6 with DIFFERENT windows per row,
+    then free-running greedy decoding."""
+    from oracle import model as OM
+    from oracle.tokens import TokenIds
+    from whisper_mlx_b200.decoding import DecodingOptions, DecodingTask
+    from whisper_mlx_b200.whisper import ModelDimensions, Whisper
+
+    dims_d = synth.DIMS["small"]
+    weights = dict(synth.random_weights(dims_d, 0, device="cuda"))
+    m = Whisper(ModelDimensions(**dims_d), weights)
+    w32 = {k: v.detach().to("cpu", torch.float32) for k, v in weights.items() if k.startswith("decoder.")}
+    del weights
+    dims = OM.ModelDimensions(**dims_d)
+    ids = TokenIds(dims.n_vocab)
+    tb = ids.timestamp_begin
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(5)
+    xa = _bf16(torch.randn(6, dims.n_audio_ctx, dims.n_audio_state, generator=g) * 0.7)
+    seq = list(ids.sot_sequence("en")) + [tb + 5, 300, 4000, 17, tb + 80, tb + 80, 900, 901, 902, tb + 200, tb + 200, 12, 13, 14, 15, 16,
+                                          tb + 400, tb + 400, 21]
+    out = {}
+    prev = os.environ.get("B200W_SMALL")
+    try:
+        for B in (1, 2, 5, 6):
+            toks = torch.tensor([seq] * B, dtype=torch.long)
+            toks[:, 6] += torch.arange(B)  # rows differ in their history too
+            os.environ["B200W_SMALL"] = "1"
+            k0 = _lib()[1].b200w_launch_count()
+            got = m.logits(toks, xa[:B].cuda()).cpu()
+            n_small = _lib()[1].b200w_launch_count() - k0
+            os.environ["B200W_SMALL"] = "0"
+            k0 = _lib()[1].b200w_launch_count()
+            big = m.logits(toks, xa[:B].cuda()).cpu()
+            n_big = _lib()[1].b200w_launch_count() - k0
+            assert n_small < n_big / 4, (n_small, n_big)  # the one-launch path really ran
+            ref, _ = OM.decoder_forward(w32, dims, toks, xa[:B].float(), policy="bf16")
+            e_paths = (got - big).abs().max().item()
+            e_ref = (got - ref).abs().max().item()
+            e_big = (big - ref).abs().max().item()
+            out[f"B{B}"] = {"small_vs_chain": e_paths, "small_vs_oracle": e_ref, "chain_vs_oracle": e_big, "launches": (n_small, n_big)}
+            assert e_ref <= LOGIT_TOL_BF16 * 1.5 and e_paths <= LOGIT_TOL_BF16 * 1.5, out
+            top2 = ref.topk(2, dim=-1).values
+            safe = (top2[..., 0] - top2[..., 1]) > 2 * e_ref
+            assert bool((got.argmax(-1) == ref.argmax(-1))[safe].all())
+        # free-running: graph-replayed one-launch steps, every token a greedy choice of the oracle up to rounding
+        os.environ["B200W_SMALL"] = "1"
+        n_steps = 40
+        res = DecodingTask(m, DecodingOptions(language="en", sample_len=n_steps)).run_features(xa[:2].cuda())
+        for i in range(2):
+            out[f"free{i}"] = _check_greedy_trajectory(w32, dims, xa[i].float(), _product_logits_fn(m, xa[i: i + 1].cuda()), res[i].tokens,
+                                                       n_steps, logit_tol=8e-2, avg_logprob=res[i].avg_logprob)
+    finally:
+        if prev is None:
+            os.environ.pop("B200W_SMALL", None)
+        else:
+            os.environ["B200W_SMALL"] = prev
+    m.release_sessions()
+    return out
+
+
 def case_decode_dual_stream():
     """Batches of >= 16 windows decode as two half-batches on two streams; the result must not depend on it."""
     from whisper_mlx_b200.decoding import DecodingOptions, DecodingTask
@@ -990,6 +1053,7 @@ CASES = {
     "decoder_tiny": case_decoder_tiny,
     "decode_tiny": case_decode_tiny,
     "large_v3_parity": case_large_v3_parity,
+    "small_batch_step": case_small_batch_step,
     "decode_dual_stream": case_decode_dual_stream,
     "transcribe_micro": case_transcribe_micro,
     "word_alignment": case_word_alignment,

@@ -15,18 +15,22 @@ for i in range(2):
     r = T.transcribe(audio, **kw)
     torch.cuda.synchronize(); dt = time.perf_counter() - t
     print(json.dumps({"seconds": dt, "rtfx": minutes * 60 / dt, "segments": len(r["segments"])}))
-# one batch-1 decode step from the CUDA graph
+# single decode steps from the CUDA graph at small batches, with the one-launch step (K13) and without it
 dm = model.dims
-xa = torch.randn(1, dm.n_audio_ctx, dm.n_audio_state, device="cuda").bfloat16()
-task = DecodingTask(model, DecodingOptions(language="en"))
-sess = DecodeSession(model, xa, 1, max_tokens=3 + 224)
-sess.set_tokens(torch.tensor(task.initial_tokens, dtype=torch.int32).repeat(1, 1))
-sess.set_filter(task._filter_params(sess), task._get_suppress_tokens())
-sess.prompt_step(len(task.initial_tokens), task.sot_index)
-sess.sample_step(); torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(50):
-    sess.sample_step()
-e1.record(); torch.cuda.synchronize()
-print(json.dumps({"batch1_step_ms": e0.elapsed_time(e1) / 50}))
+for small in ("1", "0"):
+    os.environ["B200W_SMALL"] = small
+    for B in (1, 5):
+        xa = torch.randn(B, dm.n_audio_ctx, dm.n_audio_state, device="cuda").bfloat16()
+        task = DecodingTask(model, DecodingOptions(language="en"))
+        sess = DecodeSession(model, xa, 1, max_tokens=3 + 224)
+        sess.set_tokens(torch.tensor(task.initial_tokens, dtype=torch.int32).repeat(B, 1))
+        sess.set_filter(task._filter_params(sess), task._get_suppress_tokens())
+        sess.prompt_step(len(task.initial_tokens), task.sot_index)
+        sess.sample_step(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(100):
+            sess.sample_step()
+        e1.record(); torch.cuda.synchronize()
+        print(json.dumps({"one_launch_step": small == "1", "batch": B, "step_ms": e0.elapsed_time(e1) / 100, "kernels_per_step": sess._graph_kernels}))
+        del sess

@@ -68,6 +68,13 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+// B200W_SMALL=0 keeps batches of <= 6 sequences on the chain / per-phase path instead of the one-launch step (K13)
+// (read on every call, not cached: the parity tests switch between the two paths inside one process)
+static bool small_enabled() {
+  const char* e = getenv("B200W_SMALL");
+  return !(e != nullptr && e[0] == '0');
+}
+
 // B200W_CHAIN=0 runs every small-M phase of a decode step as its own launch (the pre-chain path, kept for A/B)
 static bool chain_enabled() {
   static int v = -1;
@@ -259,6 +266,7 @@ struct Model {
   b200w_weights w;
   std::vector<b200w_enc_layer> enc;
   std::vector<b200w_dec_layer> dec;
+  b200w_dec_layer* dec_dev = nullptr;  // device copy of the decoder's pointer table (K13 walks the layers on the device)
 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -539,6 +547,7 @@ int b200w_model_create(const b200w_weights* w, b200w_model** out) {
   B200W_TRY(init_gemm2());
   B200W_TRY(init_attention());
   B200W_TRY(init_logmel());
+  B200W_TRY(init_decode_small());
   b200w_model* m = new (std::nothrow) b200w_model();
   B200W_CHECK_ARG(m != nullptr, "model_create: out of host memory");
   m->m.w = *w;
@@ -546,11 +555,23 @@ int b200w_model_create(const b200w_weights* w, b200w_model** out) {
   m->m.dec.assign(w->h_dec_layers, w->h_dec_layers + dm.n_text_layer);
   m->m.w.h_enc_layers = m->m.enc.data();
   m->m.w.h_dec_layers = m->m.dec.data();
+  // the only device memory the library owns: a copy of the decoder's pointer table (a few KB) for K13
+  const size_t tbytes = sizeof(b200w_dec_layer) * (size_t)dm.n_text_layer;
+  if (cudaMalloc(reinterpret_cast<void**>(&m->m.dec_dev), tbytes) != cudaSuccess ||
+      cudaMemcpy(m->m.dec_dev, m->m.dec.data(), tbytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_last_error("model_create: could not place the decoder layer table on the device: %s", cudaGetErrorString(cudaGetLastError()));
+    if (m->m.dec_dev) cudaFree(m->m.dec_dev);
+    delete m;
+    return kErrCuda;
+  }
   *out = m;
   return kOk;
 }
 
-void b200w_model_destroy(b200w_model* m) { delete m; }
+void b200w_model_destroy(b200w_model* m) {
+  if (m != nullptr && m->m.dec_dev != nullptr) cudaFree(m->m.dec_dev);
+  delete m;
+}
 
 size_t b200w_encoder_workspace_bytes(const b200w_model* m, int n_windows) {
   if (!m || n_windows <= 0) return 0;
@@ -671,6 +692,50 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   float* kvp = ca_split ? bf.ca_part : nullptr;
   int* kvc = ca_split ? bf.ca_cnt : nullptr;
   if (ca_split) B200W_CUDA_OK(cudaMemsetAsync(bf.ca_cnt, 0, kCaSplitUnits * sizeof(int), stream));
+  const bool one_launch = small_enabled() && decode_small_applicable(dm, B, n_q) && m.dec_dev != nullptr;
+  if (one_launch) {
+    // K13: the whole step (all layers, both attentions, final LayerNorm and the logits) as one cooperative launch
+    B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, kChainCounters * sizeof(unsigned int), stream));
+    B200W_CUDA_OK(cudaMemsetAsync(bf.ca_cnt, 0, kCaSplitUnits * sizeof(int), stream));
+    SmallArgs sa{};
+    sa.d = d;
+    sa.n_head = H;
+    sa.n_layer = dm.n_text_layer;
+    sa.n_vocab = dm.n_vocab;
+    sa.B = B;
+    sa.layers = m.dec_dev;
+    sa.tok_emb = m.w.tok_emb;
+    sa.dec_ln_g = m.w.dec_ln_g;
+    sa.dec_ln_b = m.w.dec_ln_b;
+    sa.pos = st->pos;
+    sa.finished = done;
+    sa.k_pages = static_cast<__nv_bfloat16*>(st->k_pages);
+    sa.v_pages = static_cast<__nv_bfloat16*>(st->v_pages);
+    sa.layer_page_stride = st->layer_page_stride;
+    sa.block_table = st->block_table;
+    sa.max_pages = st->max_pages;
+    sa.page_size = st->page_size;
+    sa.cross_kv = static_cast<const __nv_bfloat16*>(st->cross_kv);
+    sa.cross_layer_stride = st->cross_layer_stride;
+    sa.cross_seq_stride = (long long)T * 2 * d;
+    sa.cross_slot = st->cross_slot;
+    sa.T = T;
+    sa.x = x;
+    sa.q = static_cast<__nv_bfloat16*>(bf.qkv);
+    sa.att = static_cast<__nv_bfloat16*>(bf.att);
+    sa.qc = static_cast<__nv_bfloat16*>(bf.qc);
+    sa.mlp = static_cast<__nv_bfloat16*>(bf.mlp);
+    sa.logits = st->logits;
+    sa.logits_ld = st->logits_ld;
+    sa.ca_part = bf.ca_part;
+    sa.ca_cnt = bf.ca_cnt;
+    sa.counter = bf.counters;
+    B200W_TRY(launch_decode_small(sa, stream));
+    if (select)
+      B200W_TRY(launch_filter_argmax(st->logits, st->suppress_bits, st->tokens, st->n_tokens, st->pos, st->sum_logprob,
+                                     st->finished, B, *fp, stream));
+    return kOk;
+  }
   if (small && chained) {
     // K11: the small-M phases between the attention kernels run as three chains per layer
     //   [LN -> QKV]  SA  [out -> LN -> q]  CA  [out -> LN -> MLP1 -> MLP2 -> LN -> next layer's QKV]

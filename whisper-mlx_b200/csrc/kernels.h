@@ -103,6 +103,38 @@ int chain_add_ln(ChainParams* p, float* x, const float* part, int n_split, long 
                  const float* gamma, const float* beta, int d, __nv_bfloat16* h);
 int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------- K13 small-batch decode step
+// One cooperative launch for a whole single-token decoder step of <= kSmallMaxBatch sequences (small.cu).
+constexpr int kSmallMaxBatch = 6;
+struct SmallArgs {
+  int d, n_head, n_layer, n_vocab, B;
+  const b200w_dec_layer* layers;  // DEVICE copy of the layer table
+  const void* tok_emb;
+  const float *dec_ln_g, *dec_ln_b;
+  // decode state
+  const int* pos;
+  const int* finished;  // or null
+  __nv_bfloat16 *k_pages, *v_pages;
+  long long layer_page_stride;
+  const int* block_table;
+  int max_pages, page_size;
+  const __nv_bfloat16* cross_kv;
+  long long cross_layer_stride, cross_seq_stride;
+  const int* cross_slot;
+  int T;
+  // workspace
+  float* x;                          // (B, d) f32 residual stream, holds the embedding on entry
+  __nv_bfloat16 *q, *att, *qc, *mlp;  // (B, d) x3, (B, 4d)
+  float* logits;
+  int logits_ld;
+  float* ca_part;        // key-split cross-attention partials: (units * splits) x 66 floats
+  int* ca_cnt;           // ... arrival counters per (sequence, head), zero on entry
+  unsigned int* counter;  // grid-barrier counter, zero on entry
+};
+int init_decode_small();
+bool decode_small_applicable(const b200w_dims& dm, int n_seq, int n_q);
+int launch_decode_small(const SmallArgs& a, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------- K4 / K10 / K9
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
                      float* out_f32, cudaStream_t stream);

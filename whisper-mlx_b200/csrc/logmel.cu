@@ -168,22 +168,27 @@ logmel_kernel(const PcmT* __restrict__ pcm, long long audio_stride, long long n_
   const int f0 = (tile - audio * tiles_per_audio) * kFrames;
   float* s_samples = buf_cur;
   float* s_power = buf_cur;
+  // thread t < 200 owns column n2 = t % 25 for pairs t / 25 and t / 25 + 8 (two each: no warp waits at the barrier for
+  // a straggler with an extra pair).  Its window and twiddle values are fetched BEFORE the wait for the samples: with
+  // ~20 KB of L1 left beside 205 KB of shared memory these table reads often come from L2, and their latency then
+  // hides behind the cp.async wait and the barrier instead of stalling the first butterflies (ncu r02: long-scoreboard
+  // stalls were 18 % of the samples of this phase).
+  const int n2 = tid % 25, g = tid / 25;
+  float hw[16];
+  float4 tw[8];
+  if (tid < 200) {
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) hw[n1] = __ldg(tb.hann + 25 * n1 + n2);
+    const float4* twp = reinterpret_cast<const float4*>(tb.tw400 + n2 * 16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tw[i] = __ldg(twp + i);
+  }
   cp_async_wait_all();
   __syncthreads();  // samples of this tile have landed; the previous tile's staged rows / power are no longer read
 
   // ---- phase 1: 25 column DFT-16 per pair + W400 twiddle ------------------------------------------
-  // thread t < 200 owns column n2 = t % 25 for pairs t / 25 and t / 25 + 8 (two each: no warp waits at the barrier for
-  // a straggler with an extra pair); window and twiddles stay in registers
   if (done_tiles != nullptr && pend1 >= 0 && tid == kLmThreads - 32) wait_floor(pend1);  // (warp 7 has no column work)
   if (tid < 200) {
-    const int n2 = tid % 25, g = tid / 25;
-    float hw[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) hw[n1] = __ldg(tb.hann + 25 * n1 + n2);
-    float4 tw[8];
-    const float4* twp = reinterpret_cast<const float4*>(tb.tw400 + n2 * 16);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tw[i] = __ldg(twp + i);
 #pragma unroll 1
     for (int p = g; p < kPairs; p += 8) {
       const float* fa = s_samples + (2 * p) * kHop + n2;
