@@ -68,7 +68,7 @@ bool pdl_enabled() {
   return v != 0;
 }
 
-// B200W_SMALL=0 keeps batches of <= 6 sequences on the chain / per-phase path instead of the one-launch step (K13)
+// B200W_SMALL=0 keeps batches of <= 5 sequences on the chain / per-phase path instead of the one-launch step (K13)
 // (read on every call, not cached: the parity tests switch between the two paths inside one process)
 static bool small_enabled() {
   const char* e = getenv("B200W_SMALL");
@@ -692,7 +692,7 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   float* kvp = ca_split ? bf.ca_part : nullptr;
   int* kvc = ca_split ? bf.ca_cnt : nullptr;
   if (ca_split) B200W_CUDA_OK(cudaMemsetAsync(bf.ca_cnt, 0, kCaSplitUnits * sizeof(int), stream));
-  const bool one_launch = small_enabled() && decode_small_applicable(dm, B, n_q) && m.dec_dev != nullptr;
+  const bool one_launch = small_enabled() && decode_small_applicable(dm, B, n_q) && m.dec_dev != nullptr && st->max_pages <= 32;
   if (one_launch) {
     // K13: the whole step (all layers, both attentions, final LayerNorm and the logits) as one cooperative launch
     B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, kChainCounters * sizeof(unsigned int), stream));
@@ -971,6 +971,10 @@ int b200w_dtw(const float* matrix, long long ld, int N, int M, float* cost, sign
 }
 
 int b200w_debug_chain_mc_grid() { return chain_mc_grid(); }
+
+// development probe (tools/profile_small.py; not part of the public header): K13 stamps %globaltimer of CTA 0 at every
+// grid barrier (arrival, departure) into this device buffer of >= 2 * (8 * layers + 1) + 2 values; null switches it off
+void b200w_debug_small_timeline(void* dev_buf) { set_decode_small_timeline(static_cast<unsigned long long*>(dev_buf)); }
 
 // development probe (tools/probe_chain.py; not part of the public header): a chain of n_phases empty phases, i.e.
 // n_phases - 1 grid barriers and nothing else

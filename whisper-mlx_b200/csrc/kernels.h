@@ -105,7 +105,7 @@ int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t strea
 
 // ---------------------------------------------------------------------------------------- K13 small-batch decode step
 // One cooperative launch for a whole single-token decoder step of <= kSmallMaxBatch sequences (small.cu).
-constexpr int kSmallMaxBatch = 6;
+constexpr int kSmallMaxBatch = 5;
 struct SmallArgs {
   int d, n_head, n_layer, n_vocab, B;
   const b200w_dec_layer* layers;  // DEVICE copy of the layer table
@@ -130,7 +130,9 @@ struct SmallArgs {
   float* ca_part;        // key-split cross-attention partials: (units * splits) x 66 floats
   int* ca_cnt;           // ... arrival counters per (sequence, head), zero on entry
   unsigned int* counter;  // grid-barrier counter, zero on entry
+  unsigned long long* timeline;  // development aid: (2 * barriers + 2) time stamps of CTA 0, or null
 };
+void set_decode_small_timeline(unsigned long long* dev);
 int init_decode_small();
 bool decode_small_applicable(const b200w_dims& dm, int n_seq, int n_q);
 int launch_decode_small(const SmallArgs& a, cudaStream_t stream);
