@@ -101,6 +101,17 @@ int b200w_mel_windows(const float* mel, const float* gmax, const long long* row0
 int b200w_gemm_bf16(const void* A, long long lda, const void* W, void* C, long long ldc, const float* bias,
                     const float* resid, int M, int N, int K, int flags, void* stream);
 
+/* K14: single-token cross-attention in absorbed form -- reads the encoder states xa ((n_slots, T, d) bf16, d = 64 *
+ * n_head) instead of the cached per-layer K / V: scores = (Wk_h^T q_h) . xa_t, output = Wv_h (sum_t p_t xa_t) + bv_h,
+ * both contractions on tcgen05.  q: (n_seq, d) bf16 query projection; w_ckv / b_ckv: the layer's fused key | value
+ * projection ((2d, d) bf16, [2d] f32); slot: sequence -> row of xa; finished: sequences to skip (may be NULL);
+ * out: (n_seq, d) bf16.  Same result as b200w_decoder_cross_attention on K / V = xa W^T + b up to 16-bit rounding.
+ * Replaces UPSTREAM whisper.py::MultiHeadAttention.__call__ (cross-attention branch with kv_cache) for n_q == 1. */
+size_t b200w_absorbed_cross_attention_workspace_bytes(int n_seq, int n_head);
+int b200w_absorbed_cross_attention(const void* q, int n_seq, int n_head, const void* w_ckv, const float* b_ckv,
+                                   const void* xa, int n_slots, int T, const int* slot, const int* finished,
+                                   void* workspace, size_t workspace_bytes, void* out, void* stream);
+
 /* Split-K form for decode steps (M <= 128 rows, one row tile): the K range is cut into
  * b200w_gemm_splitk_slices(K, split_k) slices so that all SMs stream weights; slice s stores its raw fp32
  * partial product to part + s * split_stride (rows of ldp floats).  No bias / activation: the consumer

@@ -364,6 +364,42 @@ def case_decoder_attention():
     return out
 
 
+def case_absorbed_cross_attention():
+    """K14: the absorbed form (streams xa, both contractions on tcgen05) against fp32 attention over K = xa Wk^T and
+    V = xa Wv^T + bv rounded to bf16 (what the K / V cache holds), and against K8 on that cache."""
+    L, lib = _lib()
+    out = {}
+    g = torch.Generator().manual_seed(0)
+    for (B, H, T, n_slots, n_fin) in ((5, 6, 1500, 3, 0), (37, 12, 1500, 20, 9), (120, 20, 1500, 120, 0), (150, 20, 333, 40, 3)):
+        d = 64 * H
+        xa = _bf16(torch.randn(n_slots, T, d, generator=g)).cuda()
+        w = _bf16(torch.randn(2 * d, d, generator=g) / d ** 0.5).cuda()
+        bias = torch.cat([torch.zeros(d), torch.randn(d, generator=g)]).cuda()
+        q = _bf16(torch.randn(B, d, generator=g)).cuda()
+        slot = torch.randint(0, n_slots, (B,), generator=g).to(torch.int32).cuda()
+        fin = torch.zeros(B, dtype=torch.int32)
+        fin[torch.randperm(B, generator=g)[:n_fin]] = 1
+        fin = fin.cuda()
+        ws = torch.empty(lib.b200w_absorbed_cross_attention_workspace_bytes(B, H), dtype=torch.uint8, device="cuda")
+        o = torch.full((B, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+        for _ in range(2):  # twice: the arrival counters must be left ready for the next launch
+            L.check(lib.b200w_absorbed_cross_attention(L.ptr(q), B, H, L.ptr(w), L.ptr(bias), L.ptr(xa), n_slots, T, L.ptr(slot),
+                                                       L.ptr(fin), L.ptr(ws), ws.numel(), L.ptr(o), L.stream()))
+        torch.cuda.synchronize()
+        kv = (xa.float() @ w.float().T + bias).to(torch.bfloat16)            # (n_slots, T, 2d): the K | V cache
+        o8 = torch.empty((B, 1, d), dtype=torch.bfloat16, device="cuda")
+        L.check(lib.b200w_decoder_cross_attention(L.ptr(q), B, 1, H, L.ptr(kv), T * 2 * d, T, L.ptr(slot), L.ptr(o8), L.stream()))
+        torch.cuda.synchronize()
+        kvs = kv[slot.long()].float().cpu()
+        ref = _sdpa_ref(q.cpu().float()[:, None], kvs[..., :d], kvs[..., d:], H)[:, 0]
+        live = (fin == 0).cpu()
+        err = (o.cpu().float() - ref)[live].abs().max().item()
+        err8 = (o8[:, 0].cpu().float() - ref)[live].abs().max().item()
+        out[f"{B}x{H}x{T}"] = {"absorbed": err, "k8": err8}
+        assert err <= 2e-2, (B, H, T, err, err8)
+    return out
+
+
 def case_splitk_decode_ops():
     """Split-K decode GEMM + the consumers that fold the partial slabs (residual+LN, self / cross attention)."""
     L, lib = _lib()
@@ -1047,6 +1083,7 @@ CASES = {
     "encoder_attention": case_encoder_attention,
     "decoder_attention": case_decoder_attention,
     "splitk_decode_ops": case_splitk_decode_ops,
+    "absorbed_cross_attention": case_absorbed_cross_attention,
     "logmel_pcm16": case_logmel_pcm16,
     "filter_argmax": case_filter_argmax,
     "encoder_tiny": case_encoder_tiny,

@@ -78,6 +78,8 @@ SIGNATURES = {
     "b200w_logmel_finalize": (i32, [vp, vp, i32, i64, vp]),
     "b200w_mel_windows": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp]),
     "b200w_gemm_bf16": (i32, [vp, i64, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp]),
+    "b200w_absorbed_cross_attention_workspace_bytes": (sz, [i32, i32]),
+    "b200w_absorbed_cross_attention": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp, vp]),
     "b200w_gemm_bf16_splitk": (i32, [vp, i64, vp, vp, i64, i64, i32, i32, i32, i32, vp]),
     "b200w_gemm_splitk_slices": (i32, [i32, i32]),
     "b200w_residual_layernorm": (i32, [vp, vp, i32, i64, vp, vp, vp, i32, i32, vp, vp]),

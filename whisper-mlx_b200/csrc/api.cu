@@ -469,6 +469,24 @@ int b200w_decoder_cross_attention(const void* q, int n_seq, int n_q, int n_head,
                                         seq_stride, T, slot, (__nv_bfloat16*)out, (cudaStream_t)stream);
 }
 
+size_t b200w_absorbed_cross_attention_workspace_bytes(int n_seq, int n_head) {
+  if (n_seq <= 0 || n_head <= 0) return 0;
+  return absorb_workspace_bytes(n_seq, n_head, n_head * 64);
+}
+
+int b200w_absorbed_cross_attention(const void* q, int n_seq, int n_head, const void* w_ckv, const float* b_ckv,
+                                   const void* xa, int n_slots, int T, const int* slot, const int* finished,
+                                   void* workspace, size_t workspace_bytes, void* out, void* stream) {
+  B200W_CHECK_ARG(q && w_ckv && b_ckv && xa && slot && workspace && out, "absorbed_cross_attention: null argument");
+  const int d = n_head * 64;
+  B200W_CHECK_ARG(absorb_applicable(n_seq, n_head, d, T), "absorbed_cross_attention: unsupported shape");
+  B200W_CHECK_ARG(workspace_bytes >= absorb_workspace_bytes(n_seq, n_head, d), "absorbed_cross_attention: workspace too small");
+  B200W_TRY(absorb_prepare(workspace, n_seq, n_head, d, (cudaStream_t)stream));
+  return launch_absorbed_cross_attention(nullptr, 0, 0, nullptr, (const __nv_bfloat16*)q, n_seq, n_head, w_ckv, b_ckv,
+                                         (const __nv_bfloat16*)xa, n_slots, T, slot, finished, workspace,
+                                         (__nv_bfloat16*)out, (cudaStream_t)stream);
+}
+
 int b200w_gemm_bf16_splitk(const void* A, long long lda, const void* W, float* part, long long ldp, long long split_stride,
                            int M, int N, int K, int split_k, void* stream) {
   B200W_CHECK_ARG(A && W && part && split_k >= 1 && split_k <= kMaxSplit, "gemm_splitk: bad arguments");
@@ -971,6 +989,14 @@ int b200w_dtw(const float* matrix, long long ld, int N, int M, float* cost, sign
 }
 
 int b200w_debug_chain_mc_grid() { return chain_mc_grid(); }
+
+// development probe (tools/probe_absorb.py; not part of the public header): tensor-memory layouts of the two MMA shapes
+// of the absorbed cross-attention on one 64 x 128 tile
+int b200w_debug_absorb_probe(const void* x, const void* q, const void* p, unsigned int lbo, unsigned int sbo, float* dump_s,
+                             float* dump_o, void* stream) {
+  return launch_absorb_probe((const __nv_bfloat16*)x, (const __nv_bfloat16*)q, (const __nv_bfloat16*)p, lbo, sbo, dump_s,
+                             dump_o, (cudaStream_t)stream);
+}
 
 // development probe (tools/profile_small.py; not part of the public header): K13 stamps %globaltimer of CTA 0 at every
 // grid barrier (arrival, departure) into this device buffer of >= 2 * (8 * layers + 1) + 2 values; null switches it off

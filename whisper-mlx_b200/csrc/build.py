@@ -13,7 +13,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "gemm.cu", "gemm2.cu", "chain.cu", "small.cu", "align.cu", "attention.cu", "elementwise.cu", "logmel.cu"]
+SOURCES = ["api.cu", "gemm.cu", "gemm2.cu", "chain.cu", "small.cu", "absorb.cu", "align.cu", "attention.cu", "elementwise.cu",
+           "logmel.cu"]
 HEADERS = ["common.cuh", "kernels.h", "logmel_core.h", os.path.join(REPO, "include", "b200_whisper.h")]
 LIB = os.path.join(HERE, "libb200whisper.so")
 STAMP = os.path.join(HERE, ".build_stamp")
@@ -27,9 +28,10 @@ NVCC_FLAGS = [
 ] + os.environ.get("B200W_NVCC_EXTRA", "").split()  # e.g. -DB200W_CROSS_UNROLL=4 for A/B builds (tools/time_cross.py)
 
 
-def _digest() -> str:
+def _digest(sources=None) -> str:
     h = hashlib.sha256()
-    for f in SOURCES + HEADERS + [os.path.abspath(__file__)]:
+    h.update(" ".join(NVCC_FLAGS).encode())
+    for f in (SOURCES if sources is None else sources) + HEADERS + [os.path.abspath(__file__)]:
         p = f if os.path.isabs(f) else os.path.join(HERE, f)
         with open(p, "rb") as fh:
             h.update(fh.read())
@@ -48,10 +50,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return LIB
     # compile translation units in parallel, then link
-    objs, procs = [], []
+    # (an object is reused when its source, the headers and the flags are unchanged: .<name>.stamp beside it)
+    objs, procs, stamps = [], [], {}
     for src in SOURCES:
         obj = os.path.join(HERE, src.replace(".cu", ".o"))
         objs.append(obj)
+        st = os.path.join(HERE, "." + src + ".stamp")
+        dg = _digest([src])
+        if not force and not verbose and os.path.exists(obj) and os.path.exists(st) and open(st).read().strip() == dg:
+            continue
+        stamps[st] = dg
         cmd = [nvcc_path()] + [f for f in NVCC_FLAGS if f != "-shared"] + ["-c", os.path.join(HERE, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -62,6 +70,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
+    for st, dg in stamps.items():
+        with open(st, "w") as f:
+            f.write(dg)
     cmd = [nvcc_path(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     subprocess.run(cmd, check=True)
     with open(STAMP, "w") as f:

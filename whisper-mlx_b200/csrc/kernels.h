@@ -137,6 +137,22 @@ int init_decode_small();
 bool decode_small_applicable(const b200w_dims& dm, int n_seq, int n_q);
 int launch_decode_small(const SmallArgs& a, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------- K14 absorbed cross-attention
+// Single-token decode steps: the cross-attention reads the encoder states xa (n_slots, T, d) instead of the per-layer
+// K / V (absorb.cu).  q arrives as split-K slabs (+ bias) of the query projection or as bf16 (rows, d); w_ckv / b_ckv are
+// the layer's fused key | value projection; `ws` is absorb_workspace_bytes() of workspace prepared once by
+// absorb_prepare(); att (n_seq, d) bf16 receives what K8 would have written.
+int init_absorb();
+bool absorb_applicable(int n_seq, int n_head, int d, int T);
+size_t absorb_workspace_bytes(int n_seq, int n_head, int d);
+int absorb_prepare(void* ws, int n_seq, int n_head, int d, cudaStream_t stream);
+int launch_absorbed_cross_attention(const float* q_part, int n_split, long long split_stride, const float* bias_q,
+                                    const __nv_bfloat16* q_bf16, int n_seq, int n_head, const void* w_ckv,
+                                    const float* b_ckv, const __nv_bfloat16* xa, int n_slots, int T, const int* slot,
+                                    const int* finished, void* ws, __nv_bfloat16* att, cudaStream_t stream);
+int launch_absorb_probe(const __nv_bfloat16* x, const __nv_bfloat16* q, const __nv_bfloat16* p, unsigned int lbo,
+                        unsigned int sbo, float* dump_s, float* dump_o, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------- K4 / K10 / K9
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int d, __nv_bfloat16* out_bf16,
                      float* out_f32, cudaStream_t stream);
