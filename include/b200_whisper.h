@@ -297,6 +297,10 @@ typedef struct {
   float* logits_aux;    /* (n_seq, logits_ld) f32: logits at sot_index (prompt step) */
   int logits_ld;        /* >= n_vocab rounded up to 128 */
   const uint32_t* suppress_bits; /* ceil(n_vocab / 32) words, bit v set = token v suppressed */
+  const void* xa;       /* (xa_slots, n_audio_ctx, d) bf16 encoder states behind cross_kv, or NULL: when given, single-token
+                         * steps of batches >= 16 run the cross-attention in absorbed form (K14) and stream xa instead
+                         * of cross_kv (B200W_ABSORB=0 keeps K8) */
+  int xa_slots;
 } b200w_decode_state;
 
 size_t b200w_decoder_workspace_bytes(const b200w_model* m, int n_seq, int n_q);

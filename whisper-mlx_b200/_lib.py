@@ -62,7 +62,7 @@ class DecodeState(C.Structure):
                 ("sum_logprob", vp), ("finished", vp), ("no_speech", vp), ("k_pages", vp), ("v_pages", vp),
                 ("layer_page_stride", i64), ("block_table", vp), ("max_pages", i32), ("page_size", i32),
                 ("cross_kv", vp), ("cross_layer_stride", i64), ("cross_slot", vp), ("logits", vp),
-                ("logits_aux", vp), ("logits_ld", i32), ("suppress_bits", vp)]
+                ("logits_aux", vp), ("logits_ld", i32), ("suppress_bits", vp), ("xa", vp), ("xa_slots", i32)]
 
 
 # name -> (restype, argtypes); mirrors include/b200_whisper.h declaration by declaration

@@ -51,6 +51,40 @@ __device__ __forceinline__ uint64_t ab_desc(uint32_t smem_addr, uint32_t lbo_byt
   d |= (uint64_t)2 << 61;
   return d;
 }
+// true in exactly one (converged) lane of the warp; values computed before it in warp-uniform code stay in uniform
+// registers, so a tcgen05.mma issued under it needs no per-lane ELECT / R2UR loop (54 cycles per MMA otherwise)
+__device__ __forceinline__ bool ab_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void ab_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  if (ab_elect_one()) umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate ? 1u : 0u);
+}
+__device__ __forceinline__ void ab_commit(uint64_t* bar) {
+  if (ab_elect_one()) umma_commit(bar);
+}
+// barrier over the 4 softmax warps that also ORs a predicate across them
+__device__ __forceinline__ bool ab_group_or(bool v) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %1, 0;\n\t"
+      "bar.red.or.pred q, 1, 128, p;\n\t"
+      "selp.b32 %0, 1, 0, q;\n\t"
+      "}\n"
+      : "=r"(r)
+      : "r"((uint32_t)v)
+      : "memory");
+  return r != 0;
+}
 __device__ __forceinline__ float ab_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -77,6 +111,7 @@ struct AbsorbAttnArgs {
   int* cnt;              // (n_seq) arrival counters, zero on entry, left zero
   __nv_bfloat16* out;    // (n_seq, n_head, d) normalised sum_t p xa_t
   float scale;           // hd^-0.5 * log2(e)
+  long long* timeline;   // development aid: clock64 stamps of CTA 0 (8 per tile), or null
 };
 
 __global__ void __launch_bounds__(kAbThreads, 1)
@@ -100,14 +135,17 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
   int* s_nact = reinterpret_cast<int*>(tmem_slot + 1);
   int* s_last = s_nact + 1;
-  int* s_wcnt = s_last + 1;                                                  // [8] per-warp active counts
+  int* s_ncontrib = s_last + 1;
+  int* s_wcnt = s_ncontrib + 1;                                              // [8] per-warp active counts
+  int* s_sid = s_wcnt + 8;                                                   // [kAbMaxContrib] partial slots of a window
   float* s_wmax = reinterpret_cast<float*>(misc + 512);                      // [kAbMaxHeads][4]
   float* s_lsum = s_wmax + kAbMaxHeads * 4;                                  // [4][kAbMaxHeads]
   float* s_w = s_lsum + 4 * kAbMaxHeads;                                     // [kAbMaxContrib][kAbMaxHeads] merge weights
   float* s_linv = s_w + kAbMaxContrib * kAbMaxHeads;                         // [kAbMaxHeads]
   short* s_act = reinterpret_cast<short*>(misc + 512 + 4 * (8 * kAbMaxHeads + kAbMaxContrib * kAbMaxHeads + kAbMaxHeads));
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role code stays on the uniform datapath
   const int H = a.n_head, d = a.d, T = a.T;
   const int n_dblk = d >> 7;
   const int tpw = (T + kAbKeys - 1) / kAbKeys;
@@ -163,21 +201,14 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   const int w_first = lo / tpw;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------------------------------ TMA producer: xa tiles
+    // (its own thread: a slot frees when the output MMA has read it, independent of the qa ring)
     if (lane == 0) {
-      int xs = 0, qs = 0;
-      uint32_t xph = 0, qph = 0;
+      int xs = 0;
+      uint32_t xph = 0;
       for (int t = lo; t < hi; ++t) {
         const int w = t / tpw, kt = t - w * tpw, b = s_act[w], row = a.slot[b];
         for (int j = 0; j < n_dblk; ++j) {
-          mbar_wait(&qempty[qs], qph ^ 1);
-          mbar_expect_tx(&qfull[qs], kAbQSlotBytes);
-          tma_load_3d(sQ + qs * kAbQSlotBytes, &tm_q, &qfull[qs], j * 128, 0, b);
-          tma_load_3d(sQ + qs * kAbQSlotBytes + kAbQBoxBytes, &tm_q, &qfull[qs], j * 128 + 64, 0, b);
-          if (++qs == kAbQSlots) {
-            qs = 0;
-            qph ^= 1;
-          }
           mbar_wait(&xempty[xs], xph ^ 1);
           mbar_expect_tx(&xfull[xs], kAbSlotBytes);
           tma_load_3d(sX + xs * kAbSlotBytes, &tm_x, &xfull[xs], j * 128, kt * kAbKeys, row);
@@ -190,15 +221,39 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       }
     }
     __syncwarp();
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------------------------------ TMA producer: qa (from L2)
+    if (lane == 0) {
+      int qs = 0;
+      uint32_t qph = 0;
+      for (int t = lo; t < hi; ++t) {
+        const int b = s_act[t / tpw];
+        for (int j = 0; j < n_dblk; ++j) {
+          mbar_wait(&qempty[qs], qph ^ 1);
+          mbar_expect_tx(&qfull[qs], kAbQSlotBytes);
+          tma_load_3d(sQ + qs * kAbQSlotBytes, &tm_q, &qfull[qs], j * 128, 0, b);
+          tma_load_3d(sQ + qs * kAbQSlotBytes + kAbQBoxBytes, &tm_q, &qfull[qs], j * 128 + 64, 0, b);
+          if (++qs == kAbQSlots) {
+            qs = 0;
+            qph ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop (uniform control flow, descriptors in uniform registers) and one elected lane issues:
+    // issued from a divergent single-thread branch every tcgen05.mma costs a 54-cycle ELECT / R2UR loop, this way the
+    // score MMA (M 64, N 24) takes 28 cycles and the output MMA (M 128, N 32) 40 -- their shared-memory operand reads.
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(64, kAbQRows, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, kAbPRows, 1, 0);  // A = xa tile read MN-major (features x keys)
       int xs = 0, qs = 0;
       uint32_t xph = 0, qph = 0, pph = 0, ofph = 0;
       bool first_seg = true;
       const uint64_t pd = make_sw128_desc(smem_u32(sP));
+      const uint32_t x_base = smem_u32(sX), q_base = smem_u32(sQ);
       for (int t = lo; t < hi; ++t) {
         const int w = t / tpw, kt = t - w * tpw;
         const bool seg_first = (t == lo) || (kt == 0);
@@ -208,15 +263,14 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           mbar_wait(&qfull[qs], qph);
           mbar_wait(&xfull[xs], xph);
           tcgen05_fence_after();
-          const uint32_t a0 = smem_u32(sX + xs * kAbSlotBytes), b0 = smem_u32(sQ + qs * kAbQSlotBytes);
+          const uint32_t a0 = x_base + xs * kAbSlotBytes, b0 = q_base + qs * kAbQSlotBytes;
 #pragma unroll
           for (int bx = 0; bx < 2; ++bx) {
             const uint64_t ad = make_sw128_desc(a0 + bx * kAbBoxBytes), bd = make_sw128_desc(b0 + bx * kAbQBoxBytes);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16(tmem_base + kAbSCol, ad + 2 * kk, bd + 2 * kk, idesc_s, (j | bx | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) ab_mma(tmem_base + kAbSCol, ad + 2 * kk, bd + 2 * kk, idesc_s, (j | bx | kk) != 0);
           }
-          umma_commit(&qempty[qs]);
+          ab_commit(&qempty[qs]);
           if (++qs == kAbQSlots) {
             qs = 0;
             qph ^= 1;
@@ -226,7 +280,8 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             xph ^= 1;
           }
         }
-        umma_commit(s_full);
+        ab_commit(s_full);
+        if (a.timeline && cta == 0 && lane == 0 && t - lo < 64) a.timeline[(t - lo) * 8 + 0] = clock64();
         if (seg_first && !first_seg) {  // the previous window's O' has been read out of tensor memory
           mbar_wait(o_free, ofph);
           ofph ^= 1;
@@ -235,17 +290,19 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         mbar_wait(p_full, pph);
         pph ^= 1;
         tcgen05_fence_after();
+        if (a.timeline && cta == 0 && lane == 0 && t - lo < 64) a.timeline[(t - lo) * 8 + 1] = clock64();
         int sl = xs0;
         for (int j = 0; j < n_dblk; ++j) {  // O'^T tile j (128 features x 32) += xa_tile^T (128 x 64 keys) P^T
-          const uint32_t a0 = smem_u32(sX + sl * kAbSlotBytes);
+          const uint32_t a0 = x_base + sl * kAbSlotBytes;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_f16(tmem_base + kAbOCol + j * 32, ab_desc(a0 + kk * 2048, kAbBoxBytes, 1024), pd + 2 * kk, idesc_o,
-                     (!seg_first || kk != 0) ? 1u : 0u);
-          umma_commit(&xempty[sl]);
+            ab_mma(tmem_base + kAbOCol + j * 32, ab_desc(a0 + kk * 2048, kAbBoxBytes, 1024), pd + 2 * kk, idesc_o,
+                   !seg_first || kk != 0);
+          ab_commit(&xempty[sl]);
           if (++sl == kAbXSlots) sl = 0;
         }
-        if (seg_last) umma_commit(o_done);
+        if (seg_last) ab_commit(o_done);
+        if (a.timeline && cta == 0 && lane == 0 && t - lo < 64) a.timeline[(t - lo) * 8 + 2] = clock64();
       }
     }
     __syncwarp();
@@ -255,6 +312,9 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int key_l = ab_key_of_lane(q, lane);
     const bool lane_ok = ab_lane_valid(lane);
+    // byte offset of this key's element in row h of P^T: h * 128 + (((key >> 3) ^ (h & 7)) << 4) + (key & 7) * 2
+    unsigned char* p_col = sP + (key_l & 7) * 2;
+    const int key_piece = key_l >> 3;
     float m_run[kAbMaxHeads], l_part[kAbMaxHeads];
     uint32_t sph = 0, odph = 0;
     for (int t = lo; t < hi; ++t) {
@@ -268,65 +328,66 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           l_part[h] = 0.0f;
         }
       }
+      const bool tl = a.timeline && cta == 0 && gt == 0 && t - lo < 64;
       mbar_wait(s_full, sph);
       sph ^= 1;
       tcgen05_fence_after();
+      if (tl) a.timeline[(t - lo) * 8 + 3] = clock64();
       uint32_t r[32];
       tmem_ld_32x32(t_lane + kAbSCol, r);
       tmem_wait_ld();
       const bool valid = lane_ok && (kt * kAbKeys + key_l < T);
       float s[kAbMaxHeads];
+      float over = -INFINITY;  // how far this key's scores exceed the running maxima
 #pragma unroll
       for (int h = 0; h < kAbMaxHeads; ++h) {
         s[h] = valid ? __uint_as_float(r[h]) * a.scale : -INFINITY;
-        const int wm = __reduce_max_sync(0xffffffffu, ab_ord(s[h]));
-        if (lane == h) s_wmax[h * 4 + q] = ab_unord(wm);
+        if (h < H) over = fmaxf(over, s[h] - m_run[h]);
       }
-      ab_group_sync();
-      bool grow = false;
-      float m_new[kAbMaxHeads];
+      // Fast path (every tile but a window's first few): no score exceeds its head's running maximum by more than 2^8,
+      // the probabilities are taken against the (lagging) running maxima -- one barrier with an OR instead of 20 maxima.
+      if (ab_group_or(over > 8.0f)) {
 #pragma unroll
-      for (int h = 0; h < kAbMaxHeads; ++h) {
-        const float4 v = *reinterpret_cast<const float4*>(s_wmax + h * 4);
-        const float mt = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-        m_new[h] = fmaxf(m_run[h], mt);
-        grow |= (h < H) && (mt > m_run[h] + 8.0f);
-      }
-      if (seg_first) {
-#pragma unroll
-        for (int h = 0; h < kAbMaxHeads; ++h) m_run[h] = m_new[h];
-      } else if (grow) {
-        // rare after the first tiles: a maximum moved by more than 2^8 -- rescale the running sums and O' (tensor memory)
+        for (int h = 0; h < kAbMaxHeads; ++h) {
+          const int wm = __reduce_max_sync(0xffffffffu, ab_ord(s[h]));
+          if (lane == h) s_wmax[h * 4 + q] = ab_unord(wm);
+        }
+        ab_group_sync();
         float alpha[kAbMaxHeads];
 #pragma unroll
         for (int h = 0; h < kAbMaxHeads; ++h) {
-          alpha[h] = ab_exp2(m_run[h] - m_new[h]);
-          m_run[h] = m_new[h];
+          const float4 v = *reinterpret_cast<const float4*>(s_wmax + h * 4);
+          const float m_new = fmaxf(m_run[h], fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+          alpha[h] = ab_exp2(m_run[h] - m_new);  // 0 on a window's first tile (m_run = -inf)
+          m_run[h] = m_new;
           l_part[h] *= alpha[h];
         }
-        for (int j = 0; j < n_dblk; ++j) {
-          uint32_t o[32];
-          tmem_ld_32x32(t_lane + kAbOCol + j * 32, o);
-          tmem_wait_ld();
+        if (!seg_first) {  // rescale O' (tensor memory); the previous tile's output MMAs completed before S arrived
+          for (int j = 0; j < n_dblk; ++j) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_lane + kAbOCol + j * 32, o);
+            tmem_wait_ld();
 #pragma unroll
-          for (int h = 0; h < kAbMaxHeads; ++h) o[h] = __float_as_uint(__uint_as_float(o[h]) * alpha[h]);
-          tmem_st_32x32(t_lane + kAbOCol + j * 32, o);
+            for (int h = 0; h < kAbMaxHeads; ++h) o[h] = __float_as_uint(__uint_as_float(o[h]) * alpha[h]);
+            tmem_st_32x32(t_lane + kAbOCol + j * 32, o);
+          }
+          tmem_wait_st();
         }
-        tmem_wait_st();
+        ab_group_sync();  // s_wmax may be rewritten by the next slow tile
       }
+      if (tl) a.timeline[(t - lo) * 8 + 4] = clock64();
       // probabilities (allowed to reach 2^8: harmless in bf16 / fp32) -> P^T rows (heads), K-major over this tile's keys
 #pragma unroll
       for (int h = 0; h < kAbMaxHeads; ++h) {
         const float p = ab_exp2(s[h] - m_run[h]);  // 0 for masked keys
         l_part[h] += p;
-        if (lane_ok && h < H) {
-          const int piece = (key_l >> 3) ^ (h & 7);
-          *reinterpret_cast<__nv_bfloat16*>(sP + h * 128 + piece * 16 + (key_l & 7) * 2) = __float2bfloat16(p);
-        }
+        if (lane_ok && h < H)
+          *reinterpret_cast<__nv_bfloat16*>(p_col + h * 128 + ((key_piece ^ (h & 7)) << 4)) = __float2bfloat16(p);
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
       mbar_arrive(p_full);
+      if (tl) a.timeline[(t - lo) * 8 + 5] = clock64();
 
       if (seg_last) {
         // ---- flush this CTA's part of window w: (max, sum, O') -> partial slot; the last CTA of the window merges ----
@@ -336,6 +397,18 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         for (int h = 0; h < kAbMaxHeads; ++h) {
           const float v = warp_sum(l_part[h]);
           if (lane == 0) s_lsum[q * kAbMaxHeads + h] = v;
+        }
+        // contributors of window w: the CTAs whose (non-empty) tile range meets [w * tpw, (w + 1) * tpw); their partial
+        // slots go to s_sid (warp 4 tests one candidate CTA per lane)
+        const long long wlo = (long long)w * tpw, whi = wlo + tpw;
+        if (q == 0) {
+          const int c_first = (int)(((wlo + 1) * G - 1) / total), c_last = (int)((whi * G - 1) / total);
+          const int c2 = c_first + lane;
+          const long long l2 = ((long long)c2 * total) / G, h2 = ((long long)(c2 + 1) * total) / G;
+          const bool on = c2 <= c_last && h2 > l2 && l2 < whi && h2 > wlo;
+          const unsigned int mk = __ballot_sync(0xffffffffu, on);
+          if (on) s_sid[__popc(mk & ((1u << lane) - 1))] = c2 * kAbWinPerCta + (w - (int)(l2 / tpw));
+          if (lane == 0) *s_ncontrib = __popc(mk);
         }
         mbar_wait(o_done, odph);
         odph ^= 1;
@@ -352,7 +425,7 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         }
         tcgen05_fence_before();
         mbar_arrive(o_free);
-        ab_group_sync();  // s_lsum complete
+        ab_group_sync();  // s_lsum / s_sid complete
         if (gt < H) {
           float* ml = a.part_ml + (long long)slot_id * 2 * kAbMaxHeads;
           float mv = 0.0f;
@@ -362,71 +435,77 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           ml[gt] = mv;
           ml[kAbMaxHeads + gt] = (s_lsum[gt] + s_lsum[kAbMaxHeads + gt]) + (s_lsum[2 * kAbMaxHeads + gt] + s_lsum[3 * kAbMaxHeads + gt]);
         }
-        // contributors of window w: the CTAs whose (non-empty) tile range meets [w * tpw, (w + 1) * tpw)
-        const long long wlo = (long long)w * tpw, whi = wlo + tpw;
-        const int c_first = (int)(((wlo + 1) * G - 1) / total), c_last = (int)((whi * G - 1) / total);
-        int n_contrib = 0;
-        for (int c2 = c_first; c2 <= c_last; ++c2) {
-          const long long l2 = (c2 * total) / G, h2 = ((c2 + 1) * total) / G;
-          n_contrib += (h2 > l2 && l2 < whi && h2 > wlo) ? 1 : 0;
-        }
+        const int n_contrib = *s_ncontrib;
         __threadfence();
         ab_group_sync();
         if (gt == 0) *s_last = (atomicAdd(a.cnt + b, 1) == n_contrib - 1) ? 1 : 0;
         ab_group_sync();
         if (*s_last) {
           __threadfence();
-          // weights of the contributors: w_c[h] = 2^(m_c[h] - max_c m_c[h]); 1 / sum_c l_c[h] w_c[h]
+          // weights of the contributors: w_c[h] = 2^(m_c[h] - max_c m_c[h]) / sum_c l_c[h] 2^(m_c[h] - max)
           if (gt < H) {
             float M = -INFINITY;
-            int k2 = 0;
-            for (int c2 = c_first; c2 <= c_last; ++c2) {
-              const long long l2 = (c2 * total) / G, h2 = ((c2 + 1) * total) / G;
-              if (!(h2 > l2 && l2 < whi && h2 > wlo)) continue;
-              const int sid = c2 * kAbWinPerCta + (w - (int)(l2 / tpw));
-              M = fmaxf(M, __ldcg(a.part_ml + (long long)sid * 2 * kAbMaxHeads + gt));
-              ++k2;
-            }
+            for (int k2 = 0; k2 < n_contrib; ++k2) M = fmaxf(M, __ldcg(a.part_ml + (long long)s_sid[k2] * 2 * kAbMaxHeads + gt));
             float L = 0.0f;
-            k2 = 0;
-            for (int c2 = c_first; c2 <= c_last; ++c2) {
-              const long long l2 = (c2 * total) / G, h2 = ((c2 + 1) * total) / G;
-              if (!(h2 > l2 && l2 < whi && h2 > wlo)) continue;
-              const int sid = c2 * kAbWinPerCta + (w - (int)(l2 / tpw));
-              const float* ml = a.part_ml + (long long)sid * 2 * kAbMaxHeads;
+            for (int k2 = 0; k2 < n_contrib; ++k2) {
+              const float* ml = a.part_ml + (long long)s_sid[k2] * 2 * kAbMaxHeads;
               const float wc = ab_exp2(__ldcg(ml + gt) - M);
               L = fmaf(__ldcg(ml + kAbMaxHeads + gt), wc, L);
-              if (k2 < kAbMaxContrib) s_w[k2 * kAbMaxHeads + gt] = wc;
-              ++k2;
+              s_w[k2 * kAbMaxHeads + gt] = wc;
             }
-            s_linv[gt] = 1.0f / L;
+            const float linv = 1.0f / L;
+            for (int k2 = 0; k2 < n_contrib; ++k2) s_w[k2 * kAbMaxHeads + gt] *= linv;
           }
           ab_group_sync();
           __nv_bfloat16* o = a.out + (long long)b * H * d;
-          for (int h = 0; h < H; ++h) {
-            const float linv = s_linv[h];
-            for (int i0 = gt * 4; i0 < d; i0 += 128 * 4) {
+          const int n4 = H * d / 4;  // float4 columns of the (n_head, d) tile; thread gt takes gt, gt + 128, ...
+          if (n_contrib <= 3) {      // the common case: up to three contributors, all loads of four columns in flight
+            const float* p0 = a.part + (long long)s_sid[0] * H * d;
+            const float* p1 = a.part + (long long)s_sid[n_contrib > 1 ? 1 : 0] * H * d;
+            const float* p2 = a.part + (long long)s_sid[n_contrib > 2 ? 2 : 0] * H * d;
+            for (int i4 = gt; i4 < n4; i4 += 128 * 4) {
+              float4 v0[4], v1[4], v2[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = min(i4 + u * 128, n4 - 1);
+                v0[u] = __ldcg(reinterpret_cast<const float4*>(p0) + i);
+                v1[u] = __ldcg(reinterpret_cast<const float4*>(p1) + i);
+                v2[u] = __ldcg(reinterpret_cast<const float4*>(p2) + i);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = i4 + u * 128;
+                if (i < n4) {
+                  const int h = (i * 4) / d;
+                  const float w0 = s_w[h], w1 = n_contrib > 1 ? s_w[kAbMaxHeads + h] : 0.0f,
+                              w2 = n_contrib > 2 ? s_w[2 * kAbMaxHeads + h] : 0.0f;
+                  const float ox = fmaf(v2[u].x, w2, fmaf(v1[u].x, w1, v0[u].x * w0));
+                  const float oy = fmaf(v2[u].y, w2, fmaf(v1[u].y, w1, v0[u].y * w0));
+                  const float oz = fmaf(v2[u].z, w2, fmaf(v1[u].z, w1, v0[u].z * w0));
+                  const float ow = fmaf(v2[u].w, w2, fmaf(v1[u].w, w1, v0[u].w * w0));
+                  reinterpret_cast<uint2*>(o)[i] = make_uint2(pack_bf16x2(ox, oy), pack_bf16x2(oz, ow));
+                }
+              }
+            }
+          } else {
+            for (int i = gt; i < n4; i += 128) {
+              const int h = (i * 4) / d;
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              int k2 = 0;
-              for (int c2 = c_first; c2 <= c_last; ++c2) {
-                const long long l2 = (c2 * total) / G, h2 = ((c2 + 1) * total) / G;
-                if (!(h2 > l2 && l2 < whi && h2 > wlo)) continue;
-                const int sid = c2 * kAbWinPerCta + (w - (int)(l2 / tpw));
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(a.part + ((long long)sid * H + h) * d + i0));
+              for (int k2 = 0; k2 < n_contrib; ++k2) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(a.part + (long long)s_sid[k2] * H * d) + i);
                 const float wc = s_w[k2 * kAbMaxHeads + h];
                 acc.x = fmaf(v.x, wc, acc.x);
                 acc.y = fmaf(v.y, wc, acc.y);
                 acc.z = fmaf(v.z, wc, acc.z);
                 acc.w = fmaf(v.w, wc, acc.w);
-                ++k2;
               }
-              *reinterpret_cast<uint2*>(o + (long long)h * d + i0) =
-                  make_uint2(pack_bf16x2(acc.x * linv, acc.y * linv), pack_bf16x2(acc.z * linv, acc.w * linv));
+              reinterpret_cast<uint2*>(o)[i] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
             }
           }
           if (gt == 0) a.cnt[b] = 0;  // ready for the next launch
         }
-        ab_group_sync();  // s_last / s_w / s_lsum are reused by the next window
+        ab_group_sync();  // s_last / s_w / s_sid / s_lsum are reused by the next window
+        if (tl) a.timeline[(t - lo) * 8 + 6] = clock64();
       }
     }
   }
@@ -492,15 +571,21 @@ absorb_q_kernel(const __grid_constant__ CUtensorMap tm_wk, const __grid_constant
     // A tile: thread covers 4 consecutive columns of rows (tid / 16) + 8 * it; 16-byte pieces XOR-swizzled with row % 8
     const int c4 = (tid & 15) * 4, r0 = tid >> 4;
     const float4 bias = a.part ? *reinterpret_cast<const float4*>(a.bias + h * 64 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
     for (int it = 0; it < 16; ++it) {
       const int r = r0 + 8 * it, row = row0 + r;
       uint2 packed = make_uint2(0, 0);
       if (row < a.rows) {
         if (a.part) {
           float4 v = bias;
-          for (int s2 = 0; s2 < a.n_split; ++s2) {
-            const float4 p = *reinterpret_cast<const float4*>(a.part + s2 * a.split_stride + (long long)row * d + h * 64 + c4);
-            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+          float4 pp[8];
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2)
+            pp[s2] = s2 < a.n_split ? *reinterpret_cast<const float4*>(a.part + s2 * a.split_stride + (long long)row * d + h * 64 + c4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2) {
+            v.x += pp[s2].x; v.y += pp[s2].y; v.z += pp[s2].z; v.w += pp[s2].w;
           }
           packed = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
         } else {
@@ -516,19 +601,19 @@ absorb_q_kernel(const __grid_constant__ CUtensorMap tm_wk, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
 
-  if (warp == 4) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);  // B = Wk box: N (features i) contiguous
-      const uint64_t ad = make_sw128_desc(smem_u32(sA));
-      for (int i = 0; i < n_ib; ++i) {
-        mbar_wait(&wfull[i], 0);
-        tcgen05_fence_after();
+  if (uwarp == 4) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);  // B = Wk box: N (features i) contiguous
+    const uint64_t ad = make_sw128_desc(smem_u32(sA));
+    const uint32_t w_base = smem_u32(sW);
+    for (int i = 0; i < n_ib; ++i) {
+      mbar_wait(&wfull[i], 0);
+      tcgen05_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          umma_f16(tmem_base + i * 64, ad + 2 * kk, ab_desc(smem_u32(sW + i * 8192 + kk * 2048), 8192, 1024), idesc, kk != 0);
-        umma_commit(&dfull[i]);
-      }
+      for (int kk = 0; kk < 4; ++kk)
+        ab_mma(tmem_base + i * 64, ad + 2 * kk, ab_desc(w_base + i * 8192 + kk * 2048, 8192, 1024), idesc, kk != 0);
+      ab_commit(&dfull[i]);
     }
     __syncwarp();
   } else {
@@ -600,7 +685,8 @@ absorb_v_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp == 0) {
+  const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
+  if (uwarp == 0) {
     if (lane == 0) {
       int st = 0;
       uint32_t ph = 0;
@@ -616,26 +702,25 @@ absorb_v_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[st], ph);
-        tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + st * kVoStageBytes);
-        const uint64_t ad = make_sw128_desc(sa), bd = make_sw128_desc(sa + kVoABytes);
+  } else if (uwarp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
+    int st = 0;
+    uint32_t ph = 0;
+    const uint32_t s_base = smem_u32(smem);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full[st], ph);
+      tcgen05_fence_after();
+      const uint32_t sa = s_base + st * kVoStageBytes;
+      const uint64_t ad = make_sw128_desc(sa), bd = make_sw128_desc(sa + kVoABytes);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base, ad + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
-        umma_commit(&empty[st]);
-        if (++st == kVoStages) {
-          st = 0;
-          ph ^= 1;
-        }
+      for (int kk = 0; kk < 4; ++kk) ab_mma(tmem_base, ad + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0);
+      ab_commit(&empty[st]);
+      if (++st == kVoStages) {
+        st = 0;
+        ph ^= 1;
       }
-      umma_commit(dfull);
     }
+    ab_commit(dfull);
     __syncwarp();
   } else {
     const int q = warp & 3;
@@ -745,7 +830,82 @@ absorb_probe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   }
 }
 
+// Development aid (tools/probe_absorb.py --mma): cycles for `reps` back-to-back tcgen05.mma of one shape (operands are
+// whatever the shared memory holds), one commit at the end.  a_mn: A read MN-major with LBO 8192; ts: A from tensor memory.
+__global__ void __launch_bounds__(128)
+absorb_mma_bench_kernel(int m, int n, int a_mn, int ts, int reps, long long* cycles) {
+  extern __shared__ unsigned char mb_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(mb_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 98304);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 98304 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int uwarp = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform
+  if (uwarp == 1) {
+    const uint32_t idesc = make_idesc_bf16(m, n, a_mn, 0);
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 65536);
+    uint64_t ad[4], bd[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      ad[kk] = a_mn ? ab_desc(sa + kk * 2048, 8192, 1024) : make_sw128_desc(sa) + 2 * kk;
+      bd[kk] = make_sw128_desc(sb) + 2 * kk;
+    }
+    const long long t0 = clock64();
+    if (ts) {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (ab_elect_one())
+            asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;" ::"r"(tmem_base),
+                         "r"(tmem_base + 256 + kk * 8), "l"(bd[kk]), "r"(idesc)
+                         : "memory");
+      }
+    } else {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (ab_elect_one())
+            asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(tmem_base), "l"(ad[kk]), "l"(bd[kk]),
+                         "r"(idesc)
+                         : "memory");
+      }
+    }
+    const long long t1 = clock64();
+    if (ab_elect_one()) umma_commit(done);
+    __syncwarp();
+    mbar_wait(done, 0);
+    const long long t2 = clock64();
+    if (ab_elect_one()) {
+      cycles[0] = t1 - t0;
+      cycles[1] = t2 - t0;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host
+static long long* g_absorb_timeline = nullptr;
+void set_absorb_timeline(long long* dev) { g_absorb_timeline = dev; }
+
 int init_absorb() {
   static bool done = false;
   if (done) return kOk;
@@ -815,7 +975,7 @@ int launch_absorbed_cross_attention(const float* q_part, int n_split, long long 
                                     const int* finished, void* ws, __nv_bfloat16* att, cudaStream_t stream) {
   const int d = n_head * 64;
   B200W_CHECK_ARG(absorb_applicable(n_seq, n_head, d, T), "absorbed cross-attention: unsupported shape");
-  B200W_CHECK_ARG((q_part && bias_q && n_split >= 1) || q_bf16, "absorbed cross-attention: missing query input");
+  B200W_CHECK_ARG((q_part && bias_q && n_split >= 1 && n_split <= 8) || q_bf16, "absorbed cross-attention: missing query input");
   B200W_TRY(init_absorb());
   AbsorbWs w = carve_absorb(ws, n_seq, n_head, d);
   const int tiles_m = ceil_div(n_seq, 128);
@@ -862,6 +1022,7 @@ int launch_absorbed_cross_attention(const float* q_part, int n_split, long long 
     aa.cnt = w.cnt;
     aa.out = w.merged;
     aa.scale = 0.125f * kAbLog2e;
+    aa.timeline = g_absorb_timeline;
     ProfScope prof_("absorb_attn", stream);
     B200W_CUDA_OK(launch_k(absorb_attn_kernel, dim3(device_sm_count()), dim3(kAbThreads), kAbSmemBytes, stream, tx, tq, aa));
     count_launch();
@@ -875,6 +1036,12 @@ int launch_absorbed_cross_attention(const float* q_part, int n_split, long long 
                            b_ckv + d, att));
     count_launch();
   }
+  return kOk;
+}
+
+int launch_absorb_mma_bench(int m, int n, int a_mn, int ts, int reps, long long* cycles, cudaStream_t stream) {
+  B200W_CUDA_OK(cudaFuncSetAttribute(absorb_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100352));
+  B200W_CUDA_OK(launch_k(absorb_mma_bench_kernel, dim3(1), dim3(128), 100352, stream, m, n, a_mn, ts, reps, cycles));
   return kOk;
 }
 

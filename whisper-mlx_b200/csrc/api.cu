@@ -75,6 +75,17 @@ static bool small_enabled() {
   return !(e != nullptr && e[0] == '0');
 }
 
+// B200W_ABSORB=1: single-token steps of batches >= kAbsorbMinBatch run the cross-attention in absorbed form (K14)
+static bool absorb_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200W_ABSORB");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+constexpr int kAbsorbMinBatch = 16;
+
 // B200W_CHAIN=0 runs every small-M phase of a decode step as its own launch (the pre-chain path, kept for A/B)
 static bool chain_enabled() {
   static int v = -1;
@@ -305,6 +316,7 @@ struct DecBufs {
   unsigned int* counters;               // grid-barrier counters of the chain launches of one step
   float* ca_part;                       // key-split cross-attention (small batches): per-chunk (max, sum, output)
   int* ca_cnt;                          // ... and its arrival counters
+  void* absorb_ws;                      // K14 workspace (single-token steps of >= kAbsorbMinBatch sequences), or null
 };
 constexpr int kChainCounters = 256;
 constexpr int kCaSplitUnits = 80;       // the key-split form is only used while (sequence, head) pairs <= SMs / 2
@@ -327,7 +339,12 @@ static size_t carve_decoder(const b200w_dims& dm, int n_seq, int n_q, Carver& c,
   unsigned int* counters = static_cast<unsigned int*>(c.take(kChainCounters * sizeof(unsigned int)));
   float* ca_part = static_cast<float*>(c.take((size_t)kCaSplitUnits * 8 * 66 * sizeof(float)));
   int* ca_cnt = static_cast<int*>(c.take(kCaSplitUnits * sizeof(int)));
-  if (o) *o = DecBufs{x, h, qkv, att, qc, mlp, pq, p1, pr, counters, ca_part, ca_cnt};
+  void* absorb_ws = nullptr;
+  if (n_q == 1 && rows <= 256 && n_seq >= kAbsorbMinBatch && absorb_enabled() &&
+      absorb_applicable(n_seq, dm.n_text_head, (int)d, dm.n_audio_ctx))
+    absorb_ws = c.take(absorb_workspace_bytes(n_seq, dm.n_text_head, (int)d));
+  if (o) *o = DecBufs{x, h, qkv, att, qc, mlp, pq, p1, pr, counters, ca_part, ca_cnt, c.base ? absorb_ws : nullptr};
+  if (o && !c.base) o->absorb_ws = nullptr;
   return c.off;
 }
 
@@ -763,6 +780,8 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
     const int sp_qkv = plan_split_k(3 * d, d, 64, grp, wk, tm), sp_d = plan_split_k(d, d, 64, grp, wk, tm),
               sp_mlp2 = plan_split_k(d, 4 * d, 64, grp, wk, tm);
     B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, kChainCounters * sizeof(unsigned int), stream));
+    const bool absorbed = bf.absorb_ws != nullptr && st->xa != nullptr && st->xa_slots > 0 && sp_d <= 8;
+    if (absorbed) B200W_TRY(absorb_prepare(bf.absorb_ws, B, H, d, stream));
     int n_chain = 0;
     __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(bf.h);
     {
@@ -793,9 +812,14 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
         B200W_TRY(chain_add_gemm(&maps, &cp, bf.h, d, L.w_cq, d, d, sp_d, bf.part_q, d, s1, nullptr, false));
         B200W_TRY(launch_chain(maps, cp, stream));
       }
-      B200W_TRY(launch_decoder_cross_attention(nullptr, B, 1, H, ckv, (long long)T * 2 * d, T, st->cross_slot,
-                                               (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq, done, nullptr, kvp,
-                                               kvc));
+      if (absorbed)
+        B200W_TRY(launch_absorbed_cross_attention(bf.part_q, sp_d, s1, L.b_cq, nullptr, B, H, L.w_ckv, L.b_ckv,
+                                                  static_cast<const __nv_bfloat16*>(st->xa), st->xa_slots, T, st->cross_slot,
+                                                  done, bf.absorb_ws, (__nv_bfloat16*)bf.att, stream));
+      else
+        B200W_TRY(launch_decoder_cross_attention(nullptr, B, 1, H, ckv, (long long)T * 2 * d, T, st->cross_slot,
+                                                 (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq, done, nullptr, kvp,
+                                                 kvc));
       {
         const bool last = l + 1 == dm.n_text_layer;
         ChainMaps maps;
@@ -989,6 +1013,11 @@ int b200w_dtw(const float* matrix, long long ld, int N, int M, float* cost, sign
 }
 
 int b200w_debug_chain_mc_grid() { return chain_mc_grid(); }
+
+int b200w_debug_mma_bench(int m, int n, int a_mn, int ts, int reps, long long* cycles, void* stream) {
+  return launch_absorb_mma_bench(m, n, a_mn, ts, reps, cycles, (cudaStream_t)stream);
+}
+void b200w_debug_absorb_timeline(long long* dev) { set_absorb_timeline(dev); }
 
 // development probe (tools/probe_absorb.py; not part of the public header): tensor-memory layouts of the two MMA shapes
 // of the absorbed cross-attention on one 64 x 128 tile

@@ -150,6 +150,8 @@ int launch_absorbed_cross_attention(const float* q_part, int n_split, long long 
                                     const __nv_bfloat16* q_bf16, int n_seq, int n_head, const void* w_ckv,
                                     const float* b_ckv, const __nv_bfloat16* xa, int n_slots, int T, const int* slot,
                                     const int* finished, void* ws, __nv_bfloat16* att, cudaStream_t stream);
+int launch_absorb_mma_bench(int m, int n, int a_mn, int ts, int reps, long long* cycles, cudaStream_t stream);
+void set_absorb_timeline(long long* dev);  // development aid: 64 x 8 clock64 stamps of CTA 0, or null
 int launch_absorb_probe(const __nv_bfloat16* x, const __nv_bfloat16* q, const __nv_bfloat16* p, unsigned int lbo,
                         unsigned int sbo, float* dump_s, float* dump_o, cudaStream_t stream);
 

@@ -131,7 +131,10 @@ class DecodeSession:
             _lib.ptr(self.sum_logprob), _lib.ptr(self.finished), _lib.ptr(self.no_speech), _lib.ptr(self.k_pages),
             _lib.ptr(self.v_pages), self.k_pages.stride(0), _lib.ptr(self.block_table), self.max_pages, ps,
             _lib.ptr(self.cross), self.cross.stride(0), _lib.ptr(self.cross_slot), _lib.ptr(self.logits),
-            _lib.ptr(self.logits_aux), ld, _lib.ptr(self.suppress_bits))
+            _lib.ptr(self.logits_aux), ld, _lib.ptr(self.suppress_bits), None, 0)
+        self.xa: Optional[torch.Tensor] = None
+        if audio_features is not None and cross_kv is None:
+            self._keep_xa(audio_features)
 
     # -- setup -------------------------------------------------------------------------------------
     def load(self, audio_features: torch.Tensor) -> None:
@@ -140,6 +143,17 @@ class DecodeSession:
             audio_features = audio_features[None]
         assert audio_features.shape[0] == self.n_audio
         self.model.cross_kv(audio_features.to(torch.bfloat16), out=self.cross)
+        self._keep_xa(audio_features)
+
+    def _keep_xa(self, audio_features: torch.Tensor) -> None:
+        """The encoder states behind the cross K/V stay with the session: the absorbed cross-attention (K14) of large
+        batches reads them instead of the per-layer K / V."""
+        xa = audio_features.to(torch.bfloat16)
+        if self.xa is None or self.xa.shape != xa.shape:
+            self.xa = torch.empty_like(xa, memory_format=torch.contiguous_format)
+        self.xa.copy_(xa)
+        self.state.xa = self.xa.data_ptr()
+        self.state.xa_slots = self.n_audio
 
     def set_tokens(self, tokens: torch.Tensor) -> None:
         """Load token histories (B, n); nothing is cached yet."""
