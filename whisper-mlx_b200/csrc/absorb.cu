@@ -51,24 +51,11 @@ __device__ __forceinline__ uint64_t ab_desc(uint32_t smem_addr, uint32_t lbo_byt
   d |= (uint64_t)2 << 61;
   return d;
 }
-// true in exactly one (converged) lane of the warp; values computed before it in warp-uniform code stay in uniform
-// registers, so a tcgen05.mma issued under it needs no per-lane ELECT / R2UR loop (54 cycles per MMA otherwise)
-__device__ __forceinline__ bool ab_elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void ab_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-  if (ab_elect_one()) umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate ? 1u : 0u);
+  if (elect_one()) umma_f16(d_tmem, a_desc, b_desc, idesc, accumulate ? 1u : 0u);
 }
 __device__ __forceinline__ void ab_commit(uint64_t* bar) {
-  if (ab_elect_one()) umma_commit(bar);
+  if (elect_one()) umma_commit(bar);
 }
 // barrier over the 4 softmax warps that also ORs a predicate across them
 __device__ __forceinline__ bool ab_group_or(bool v) {
@@ -870,7 +857,7 @@ absorb_mma_bench_kernel(int m, int n, int a_mn, int ts, int reps, long long* cyc
       for (int r = 0; r < reps; ++r) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          if (ab_elect_one())
+          if (elect_one())
             asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, 1;" ::"r"(tmem_base),
                          "r"(tmem_base + 256 + kk * 8), "l"(bd[kk]), "r"(idesc)
                          : "memory");
@@ -879,18 +866,18 @@ absorb_mma_bench_kernel(int m, int n, int a_mn, int ts, int reps, long long* cyc
       for (int r = 0; r < reps; ++r) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          if (ab_elect_one())
+          if (elect_one())
             asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(tmem_base), "l"(ad[kk]), "l"(bd[kk]),
                          "r"(idesc)
                          : "memory");
       }
     }
     const long long t1 = clock64();
-    if (ab_elect_one()) umma_commit(done);
+    if (elect_one()) umma_commit(done);
     __syncwarp();
     mbar_wait(done, 0);
     const long long t2 = clock64();
-    if (ab_elect_one()) {
+    if (elect_one()) {
       cycles[0] = t1 - t0;
       cycles[1] = t2 - t0;
     }

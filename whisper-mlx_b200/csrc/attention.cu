@@ -85,6 +85,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool w0 = __shfl_sync(0xffffffffu, warp, 0) == 0;  // provably warp-uniform: warp 0 issues every MMA (one elected lane)
   const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
   const int nkv = (T + BKV - 1) / BKV;
 
@@ -148,15 +149,16 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
   float m_used = -INFINITY, l_run = 0.0f;
   const int row = tid;  // query row within the tile == TMEM lane
 
-  if (tid == 0) {
+  if (w0) {
     mbar_wait(bar_q, 0);
     mbar_wait(&bar_k[0], 0);
     tcgen05_fence_after();
     const uint64_t qd = make_sw128_desc(smem_u32(sQ));
     const uint64_t kd = make_sw128_desc(smem_u32(sK));
 #pragma unroll
-    for (int k = 0; k < kHd / 16; ++k) umma_f16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-    umma_commit(bar_s);
+    for (int k = 0; k < kHd / 16; ++k)
+      if (elect_one()) umma_f16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+    if (elect_one()) umma_commit(bar_s);
   }
   __syncwarp();
 
@@ -172,23 +174,25 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
 #pragma unroll
       for (int i = 0; i < BKV; ++i) sc[i] = __uint_as_float(r[i]);
     }
-    auto issue_next_s = [&]() {  // thread 0 only
+    auto issue_next_s = [&]() {  // all of warp 0
       if (j + 1 < nkv) {
         mbar_wait(&bar_k[(j + 1) & 1], ((j + 1) >> 1) & 1);
         tcgen05_fence_after();
         const uint64_t qd = make_sw128_desc(smem_u32(sQ));
         const uint64_t kd = make_sw128_desc(smem_u32(sK + ((j + 1) & 1) * Cfg::kKvTileBytes));
 #pragma unroll
-        for (int k = 0; k < kHd / 16; ++k) umma_f16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-        umma_commit(bar_s);
+        for (int k = 0; k < kHd / 16; ++k)
+          if (elect_one()) umma_f16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+        if (elect_one()) umma_commit(bar_s);
       }
     };
     if constexpr (!PT) {
       tcgen05_fence_before();
       __syncthreads();  // every warp holds its S(j) rows: the S columns and K buffer j & 1 are free
-      if (tid == 0) {
+      if (w0) {
         tcgen05_fence_after();
-        if (j + 2 < nkv) load_k(j + 2);
+        if (tid == 0 && j + 2 < nkv) load_k(j + 2);
+        __syncwarp();
         issue_next_s();
       }
     } else {
@@ -272,22 +276,23 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_
     l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
     tcgen05_fence_before();
     __syncthreads();  // P(j) (and a rescaled O) are in place
-    if (tid == 0) {
+    if (w0) {
       tcgen05_fence_after();
       mbar_wait(&bar_v[j & 1], (j >> 1) & 1);
       tcgen05_fence_after();
+      const uint32_t v_base = smem_u32(sV + (j & 1) * Cfg::kKvTileBytes);
 #pragma unroll
       for (int k = 0; k < BKV / 16; ++k) {
-        const uint64_t vd = make_sw128_desc_lbo(smem_u32(sV + (j & 1) * Cfg::kKvTileBytes + k * 2048), BKV * 128);
+        const uint64_t vd = make_sw128_desc_lbo(v_base + k * 2048, BKV * 128);
         if constexpr (PT) {
-          umma_f16_ts(tmem_base + BKV, tmem_base + k * 8, vd, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          if (elect_one()) umma_f16_ts(tmem_base + BKV, tmem_base + k * 8, vd, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
         } else {
           const uint64_t pd = make_sw128_desc(smem_u32(sP + (k >> 2) * kQTileBytes)) + 2 * (k & 3);
-          umma_f16(tmem_base + BKV, pd, vd, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
+          if (elect_one()) umma_f16(tmem_base + BKV, pd, vd, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
         }
       }
-      umma_commit(bar_o);
-      // the tensor pipe runs this thread's MMAs in order: S(j+1) may overwrite the P columns only after P V(j) read them
+      if (elect_one()) umma_commit(bar_o);
+      // the tensor pipe runs the warp's MMAs in order: S(j+1) may overwrite the P columns only after P V(j) read them
       if constexpr (PT) issue_next_s();
     }
     __syncwarp();

@@ -297,6 +297,22 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// True in exactly one lane of a converged warp.  A tcgen05.mma issued under it from warp-uniform code (the whole warp
+// walks the loop, operands computed by all lanes) takes its descriptors from uniform registers; issued from a divergent
+// `if (threadIdx.x == 0)` branch the compiler wraps every MMA in an ELECT / R2UR / branch loop that costs 54 cycles per
+// instruction (measured, tools/mma_bench.py: M 128 x N 64 SS 48 cycles, TS 32 cycles when issued this way).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base_lane + i)

@@ -125,13 +125,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (__shfl_sync(0xffffffffu, warp, 0) == 1) {
+    // The whole warp walks the loop and one elected lane issues (elect_one(), common.cuh): the descriptors then live in
+    // uniform registers and the four MMAs of a K block issue back to back (issued from a divergent single-thread branch
+    // each cost a 54-cycle ELECT / R2UR loop -- as long as a 128 x 128 x 16 MMA itself).
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t s_base = smem_u32(smem);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -141,21 +145,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sa = s_base + stage * Cfg::kStageBytes;
           const uint64_t a_desc = make_sw128_desc(sa);
           const uint64_t b_desc = make_sw128_desc(sa + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // +32 bytes along the swizzled row per K=16 slice -> +2 in the (addr >> 4) field
-            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb_begin || k != 0) ? 1u : 0u);
+            if (elect_one()) umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb > kb_begin || k != 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (elect_one()) umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if (elect_one()) umma_commit(&tmem_full_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
