@@ -370,7 +370,7 @@ def case_absorbed_cross_attention():
     L, lib = _lib()
     out = {}
     g = torch.Generator().manual_seed(0)
-    for (B, H, T, n_slots, n_fin) in ((5, 6, 1500, 3, 0), (37, 12, 1500, 20, 9), (120, 20, 1500, 120, 0), (150, 20, 333, 40, 3)):
+    for (B, H, T, n_slots, n_fin) in ((5, 8, 1500, 3, 0), (37, 12, 1500, 20, 9), (120, 20, 1500, 120, 0), (150, 20, 333, 40, 3), (200, 16, 1500, 7, 11)):
         d = 64 * H
         xa = _bf16(torch.randn(n_slots, T, d, generator=g)).cuda()
         w = _bf16(torch.randn(2 * d, d, generator=g) / d ** 0.5).cuda()

@@ -26,20 +26,22 @@ constexpr int kAbPRows = 32;                      // rows of P^T: N of the outpu
 constexpr int kAbMaxHeads = 20;
 constexpr int kAbBoxBytes = kAbKeys * 128;        // 64 keys x 64 features
 constexpr int kAbSlotBytes = 2 * kAbBoxBytes;     // 64 keys x 128 features (one M tile of the output MMA)
-constexpr int kAbXSlots = 12;
+constexpr int kAbXSlots = 10;
 constexpr int kAbQBoxBytes = kAbQRows * 128;
 constexpr int kAbQSlotBytes = 2 * kAbQBoxBytes;
-constexpr int kAbQSlots = 3;
+constexpr int kAbQSlots = 6;
 constexpr int kAbPBytes = kAbPRows * 128;
-constexpr int kAbMiscBytes = 8192;
+constexpr int kAbMiscBytes = 4096;
+constexpr int kAbExchBytes = 2 * kAbKeys * kAbMaxHeads * 4;  // the peer CTA's partial scores of two tiles
 constexpr int kAbThreads = 256;                   // warp 0 TMA, warp 1 MMA, warp 2 TMEM, warps 4-7 softmax / epilogue
-constexpr int kAbMaxDblk = 10;                    // d <= 1280
-constexpr int kAbTmemCols = 512;
-constexpr int kAbSCol = 0;                        // S^T: 24 columns
-constexpr int kAbOCol = 32;                       // O'^T tiles: d / 128 x 32 columns
-constexpr int kAbSmemBytes = kAbXSlots * kAbSlotBytes + kAbQSlots * kAbQSlotBytes + kAbPBytes + kAbMiscBytes + 1024;
-constexpr int kAbWinPerCta = 4;                   // partial slots per CTA (windows a CTA's tile range can touch)
-constexpr int kAbMaxContrib = 32;
+constexpr int kAbMaxDblk = 5;                     // 128-feature blocks per CTA: d / 2 <= 640
+constexpr int kAbTmemCols = 256;
+constexpr int kAbSCol = 0;                        // S^T of two tiles: 2 x 32 columns (24 used)
+constexpr int kAbOCol = 64;                       // O'^T tiles: d / 256 x 32 columns
+constexpr int kAbSmemBytes = kAbXSlots * kAbSlotBytes + kAbQSlots * kAbQSlotBytes + 2 * kAbPBytes + kAbExchBytes + kAbMiscBytes + 1024;
+static_assert(kAbSmemBytes <= 232448, "shared memory budget of one CTA per SM");
+constexpr int kAbMaxUnits = 512;                  // partial slots: n_seq * nsplit stays below this when nsplit > 1
+constexpr int kAbMaxContrib = 24;
 constexpr int kAbMaxSeq = 256;
 
 __device__ __forceinline__ uint64_t ab_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -93,14 +95,59 @@ struct AbsorbAttnArgs {
   int n_seq, n_head, d, T;
   const int* finished;   // or null
   const int* slot;       // sequence -> row of xa
-  float* part;           // (grid * kAbWinPerCta, n_head, d) f32 unnormalised partial outputs
-  float* part_ml;        // (grid * kAbWinPerCta, 2, kAbMaxHeads) running maximum (exp2 domain) and sum
+  float* part;           // (live sequences * nsplit, n_head, d) f32 unnormalised partial outputs (nsplit > 1)
+  float* part_ml;        // (live sequences * nsplit, 2, kAbMaxHeads) running maximum (exp2 domain) and sum
   int* cnt;              // (n_seq) arrival counters, zero on entry, left zero
   __nv_bfloat16* out;    // (n_seq, n_head, d) normalised sum_t p xa_t
   float scale;           // hd^-0.5 * log2(e)
+  int nsplit;            // chunks per window (a function of n_seq only: results do not depend on the batch position)
   long long* timeline;   // development aid: clock64 stamps of CTA 0 (8 per tile), or null
 };
 
+__device__ __forceinline__ uint32_t ab_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void ab_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t ab_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void ab_st_remote_v4(uint32_t cluster_addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void ab_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire: the peer's st.shared::cluster data is visible afterwards
+__device__ __forceinline__ void ab_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+// A CTA PAIR (cluster of 2) works on one unit: CTA r holds the features [r d/2, (r+1) d/2) of every key tile (80 KB per
+// tile for d = 1280, so that two tiles and more are in flight / resident instead of one), computes the partial scores
+// over its features, the two exchange them through distributed shared memory, both run the (identical) softmax and each
+// accumulates its half of O'.  The score MMAs of tile t+1 are issued before the output MMAs of tile t.
 __global__ void __launch_bounds__(kAbThreads, 1)
 absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_q,
                    const __grid_constant__ AbsorbAttnArgs a) {
@@ -110,31 +157,34 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   unsigned char* sX = smem;
   unsigned char* sQ = sX + kAbXSlots * kAbSlotBytes;
   unsigned char* sP = sQ + kAbQSlots * kAbQSlotBytes;
-  unsigned char* misc = sP + kAbPBytes;
+  float* sE = reinterpret_cast<float*>(sP + 2 * kAbPBytes);      // [2][64 keys][kAbMaxHeads]: the peer's partial scores
+  unsigned char* misc = reinterpret_cast<unsigned char*>(sE) + kAbExchBytes;
   uint64_t* xfull = reinterpret_cast<uint64_t*>(misc);
   uint64_t* xempty = xfull + kAbXSlots;
   uint64_t* qfull = xempty + kAbXSlots;
   uint64_t* qempty = qfull + kAbQSlots;
-  uint64_t* s_full = qempty + kAbQSlots;
-  uint64_t* p_full = s_full + 1;
+  uint64_t* s_full = qempty + kAbQSlots;   // [2]
+  uint64_t* e_full = s_full + 2;           // [2]
+  uint64_t* p_full = e_full + 2;
   uint64_t* o_done = p_full + 1;
   uint64_t* o_free = o_done + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint64_t* o_sync = o_free + 1;           // completes once per tile, when its output MMAs have finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_sync + 1);
   int* s_nact = reinterpret_cast<int*>(tmem_slot + 1);
   int* s_last = s_nact + 1;
-  int* s_ncontrib = s_last + 1;
-  int* s_wcnt = s_ncontrib + 1;                                              // [8] per-warp active counts
-  int* s_sid = s_wcnt + 8;                                                   // [kAbMaxContrib] partial slots of a window
+  int* s_wcnt = s_last + 1;                                                  // [8] per-warp active counts
   float* s_wmax = reinterpret_cast<float*>(misc + 512);                      // [kAbMaxHeads][4]
   float* s_lsum = s_wmax + kAbMaxHeads * 4;                                  // [4][kAbMaxHeads]
   float* s_w = s_lsum + 4 * kAbMaxHeads;                                     // [kAbMaxContrib][kAbMaxHeads] merge weights
-  float* s_linv = s_w + kAbMaxContrib * kAbMaxHeads;                         // [kAbMaxHeads]
-  short* s_act = reinterpret_cast<short*>(misc + 512 + 4 * (8 * kAbMaxHeads + kAbMaxContrib * kAbMaxHeads + kAbMaxHeads));
+  short* s_act = reinterpret_cast<short*>(misc + 512 + 4 * (8 * kAbMaxHeads + kAbMaxContrib * kAbMaxHeads));
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role code stays on the uniform datapath
   const int H = a.n_head, d = a.d, T = a.T;
-  const int n_dblk = d >> 7;
+  const int rank = (int)ab_cluster_rank(), peer = rank ^ 1;
+  const int dh = d >> 1;             // features of this CTA
+  const int n_dblk = dh >> 7;        // 128-feature blocks of this CTA
+  const int f0 = rank * dh;
   const int tpw = (T + kAbKeys - 1) / kAbKeys;
 
   if (tid == 0) {
@@ -148,14 +198,18 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
       mbar_init(&qfull[i], 1);
       mbar_init(&qempty[i], 1);
     }
-    mbar_init(s_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&e_full[i], 1);    // one arrive from the peer per tile (after its 128 softmax threads have stored)
+    }
     mbar_init(p_full, 128);
     mbar_init(o_done, 1);
     mbar_init(o_free, 128);
+    mbar_init(o_sync, 1);
     fence_barrier_init();
   }
   // rows >= n_head of P^T stay zero for the whole kernel
-  for (int i = tid; i < kAbPBytes / 16; i += kAbThreads) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * kAbPBytes / 16; i += kAbThreads) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
   // ordered list of the sequences that still decode
   {
     const int i = tid;  // n_seq <= 256 == blockDim
@@ -179,30 +233,37 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   fence_proxy_async_smem();
   tcgen05_fence_before();
   __syncthreads();
+  ab_cluster_sync();  // the peer's barriers exist before anything is sent to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_act = *s_nact;
-  const long long total = (long long)n_act * tpw;
-  const int G = gridDim.x, cta = blockIdx.x;
-  const int lo = (int)((cta * total) / G), hi = (int)(((cta + 1) * total) / G);
-  const int w_first = lo / tpw;
+  // Work units: (live sequence, chunk of its key tiles).  Every window is cut at the SAME tile boundaries whatever the
+  // batch holds (nsplit comes from the host, a function of n_seq only), so a window's result does not depend on its
+  // position in the batch or on which other sequences have finished.  nsplit == 1: the unit owns the whole window and
+  // writes the normalised output itself; else partial (max, sum, O') per chunk, merged by the last chunk to finish.
+  const int tpc = (tpw + a.nsplit - 1) / a.nsplit;   // tiles per chunk
+  const int nsplit = (tpw + tpc - 1) / tpc;           // chunks that actually hold tiles
+  const int n_units = n_act * nsplit;
+  const int G = gridDim.x >> 1, cl = blockIdx.x >> 1;  // clusters; both CTAs of a pair walk the same units
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------ TMA producer: xa tiles
-    // (its own thread: a slot frees when the output MMA has read it, independent of the qa ring)
     if (lane == 0) {
       int xs = 0;
       uint32_t xph = 0;
-      for (int t = lo; t < hi; ++t) {
-        const int w = t / tpw, kt = t - w * tpw, b = s_act[w], row = a.slot[b];
-        for (int j = 0; j < n_dblk; ++j) {
-          mbar_wait(&xempty[xs], xph ^ 1);
-          mbar_expect_tx(&xfull[xs], kAbSlotBytes);
-          tma_load_3d(sX + xs * kAbSlotBytes, &tm_x, &xfull[xs], j * 128, kt * kAbKeys, row);
-          tma_load_3d(sX + xs * kAbSlotBytes + kAbBoxBytes, &tm_x, &xfull[xs], j * 128 + 64, kt * kAbKeys, row);
-          if (++xs == kAbXSlots) {
-            xs = 0;
-            xph ^= 1;
+      for (int u = cl; u < n_units; u += G) {
+        const int w = u / nsplit, chunk = u - w * nsplit, row = a.slot[s_act[w]];
+        const int kt1 = min(tpw, (chunk + 1) * tpc);
+        for (int kt = chunk * tpc; kt < kt1; ++kt) {
+          for (int j = 0; j < n_dblk; ++j) {
+            mbar_wait(&xempty[xs], xph ^ 1);
+            mbar_expect_tx(&xfull[xs], kAbSlotBytes);
+            tma_load_3d(sX + xs * kAbSlotBytes, &tm_x, &xfull[xs], f0 + j * 128, kt * kAbKeys, row);
+            tma_load_3d(sX + xs * kAbSlotBytes + kAbBoxBytes, &tm_x, &xfull[xs], f0 + j * 128 + 64, kt * kAbKeys, row);
+            if (++xs == kAbXSlots) {
+              xs = 0;
+              xph ^= 1;
+            }
           }
         }
       }
@@ -213,16 +274,19 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     if (lane == 0) {
       int qs = 0;
       uint32_t qph = 0;
-      for (int t = lo; t < hi; ++t) {
-        const int b = s_act[t / tpw];
-        for (int j = 0; j < n_dblk; ++j) {
-          mbar_wait(&qempty[qs], qph ^ 1);
-          mbar_expect_tx(&qfull[qs], kAbQSlotBytes);
-          tma_load_3d(sQ + qs * kAbQSlotBytes, &tm_q, &qfull[qs], j * 128, 0, b);
-          tma_load_3d(sQ + qs * kAbQSlotBytes + kAbQBoxBytes, &tm_q, &qfull[qs], j * 128 + 64, 0, b);
-          if (++qs == kAbQSlots) {
-            qs = 0;
-            qph ^= 1;
+      for (int u = cl; u < n_units; u += G) {
+        const int w = u / nsplit, chunk = u - w * nsplit, b = s_act[w];
+        const int kt1 = min(tpw, (chunk + 1) * tpc);
+        for (int kt = chunk * tpc; kt < kt1; ++kt) {
+          for (int j = 0; j < n_dblk; ++j) {
+            mbar_wait(&qempty[qs], qph ^ 1);
+            mbar_expect_tx(&qfull[qs], kAbQSlotBytes);
+            tma_load_3d(sQ + qs * kAbQSlotBytes, &tm_q, &qfull[qs], f0 + j * 128, 0, b);
+            tma_load_3d(sQ + qs * kAbQSlotBytes + kAbQBoxBytes, &tm_q, &qfull[qs], f0 + j * 128 + 64, 0, b);
+            if (++qs == kAbQSlots) {
+              qs = 0;
+              qph ^= 1;
+            }
           }
         }
       }
@@ -233,20 +297,16 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     // The whole warp walks the loop (uniform control flow, descriptors in uniform registers) and one elected lane issues:
     // issued from a divergent single-thread branch every tcgen05.mma costs a 54-cycle ELECT / R2UR loop, this way the
     // score MMA (M 64, N 24) takes 28 cycles and the output MMA (M 128, N 32) 40 -- their shared-memory operand reads.
+    // Order: scores(t + 1) are issued before output(t), so they run while the softmax warps work on tile t.
     {
       constexpr uint32_t idesc_s = make_idesc_bf16(64, kAbQRows, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, kAbPRows, 1, 0);  // A = xa tile read MN-major (features x keys)
       int xs = 0, qs = 0;
       uint32_t xph = 0, qph = 0, pph = 0, ofph = 0;
-      bool first_seg = true;
-      const uint64_t pd = make_sw128_desc(smem_u32(sP));
-      const uint32_t x_base = smem_u32(sX), q_base = smem_u32(sQ);
-      for (int t = lo; t < hi; ++t) {
-        const int w = t / tpw, kt = t - w * tpw;
-        const bool seg_first = (t == lo) || (kt == 0);
-        const bool seg_last = (t + 1 == hi) || (kt + 1 == tpw);
-        const int xs0 = xs;
-        for (int j = 0; j < n_dblk; ++j) {  // S^T (64 keys x 24) = xa_tile (64 x d) qa^T
+      const uint32_t x_base = smem_u32(sX), q_base = smem_u32(sQ), p_base = smem_u32(sP);
+      auto scores = [&](int sbuf) -> int {  // S^T (64 keys x 24) = xa_tile (64 x d/2) qa^T; returns the tile's first slot
+        const int first = xs;
+        for (int j = 0; j < n_dblk; ++j) {
           mbar_wait(&qfull[qs], qph);
           mbar_wait(&xfull[xs], xph);
           tcgen05_fence_after();
@@ -255,7 +315,8 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           for (int bx = 0; bx < 2; ++bx) {
             const uint64_t ad = make_sw128_desc(a0 + bx * kAbBoxBytes), bd = make_sw128_desc(b0 + bx * kAbQBoxBytes);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) ab_mma(tmem_base + kAbSCol, ad + 2 * kk, bd + 2 * kk, idesc_s, (j | bx | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk)
+              ab_mma(tmem_base + kAbSCol + sbuf * 32, ad + 2 * kk, bd + 2 * kk, idesc_s, (j | bx | kk) != 0);
           }
           ab_commit(&qempty[qs]);
           if (++qs == kAbQSlots) {
@@ -267,18 +328,66 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             xph ^= 1;
           }
         }
-        ab_commit(s_full);
-        if (a.timeline && cta == 0 && lane == 0 && t - lo < 64) a.timeline[(t - lo) * 8 + 0] = clock64();
-        if (seg_first && !first_seg) {  // the previous window's O' has been read out of tensor memory
+        ab_commit(&s_full[sbuf]);
+        return first;
+      };
+      // the CTA's tiles as one sequence: (unit, tile) pairs; `nu`, `nkt` are the tile after `u`, `kt`
+      int u = cl, kt = 0, kt1 = 0, ti = 0;
+      if (u < n_units) {
+        const int chunk = u % nsplit;
+        kt = chunk * tpc;
+        kt1 = min(tpw, kt + tpc);
+      }
+      int slot_cur = 0, slot_nxt = 0;
+      bool have_cur = false, have_nxt = false;  // scores of the current / next tile already issued
+      bool first_unit = true;
+      while (u < n_units) {
+        const bool seg_first = kt == (u % nsplit) * tpc, seg_last = kt + 1 == kt1;
+        int nu = u, nkt = kt + 1, nkt1 = kt1;
+        if (nkt == kt1) {
+          nu = u + G;
+          if (nu < n_units) {
+            const int chunk = nu % nsplit;
+            nkt = chunk * tpc;
+            nkt1 = min(tpw, nkt + tpc);
+          }
+        }
+        if (!have_cur) {
+          slot_cur = scores(ti & 1);
+          have_cur = true;
+        }
+        // Look ahead only when it costs nothing: the next tile's features have landed already.  (Issued unconditionally,
+        // the next tile's scores would make this tile's output MMAs -- which free the slots the tile after needs -- wait
+        // for data that is still in flight.)
+        if (nu < n_units && !have_nxt) {
+          int last = xs + n_dblk - 1;
+          uint32_t lph = xph;
+          if (last >= kAbXSlots) {
+            last -= kAbXSlots;
+            lph ^= 1;
+          }
+          int qlast = qs + n_dblk - 1;
+          uint32_t qlph = qph;
+          if (qlast >= kAbQSlots) {
+            qlast -= kAbQSlots;
+            qlph ^= 1;
+          }
+          if (mbar_try_wait(&xfull[last], lph) && mbar_try_wait(&qfull[qlast], qlph)) {
+            slot_nxt = scores((ti + 1) & 1);
+            have_nxt = true;
+          }
+        }
+        if (a.timeline && blockIdx.x == 0 && lane == 0 && ti < 64) a.timeline[ti * 8 + 0] = clock64();
+        if (seg_first && !first_unit) {  // the previous unit's O' has been read out of tensor memory
           mbar_wait(o_free, ofph);
           ofph ^= 1;
         }
-        first_seg = false;
         mbar_wait(p_full, pph);
         pph ^= 1;
         tcgen05_fence_after();
-        if (a.timeline && cta == 0 && lane == 0 && t - lo < 64) a.timeline[(t - lo) * 8 + 1] = clock64();
-        int sl = xs0;
+        if (a.timeline && blockIdx.x == 0 && lane == 0 && ti < 64) a.timeline[ti * 8 + 1] = clock64();
+        int sl = slot_cur;
+        const uint64_t pd = make_sw128_desc(p_base + (ti & 1) * kAbPBytes);
         for (int j = 0; j < n_dblk; ++j) {  // O'^T tile j (128 features x 32) += xa_tile^T (128 x 64 keys) P^T
           const uint32_t a0 = x_base + sl * kAbSlotBytes;
 #pragma unroll
@@ -288,8 +397,19 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
           ab_commit(&xempty[sl]);
           if (++sl == kAbXSlots) sl = 0;
         }
-        if (seg_last) ab_commit(o_done);
-        if (a.timeline && cta == 0 && lane == 0 && t - lo < 64) a.timeline[(t - lo) * 8 + 2] = clock64();
+        ab_commit(o_sync);
+        if (seg_last) {
+          ab_commit(o_done);
+          first_unit = false;
+        }
+        if (a.timeline && blockIdx.x == 0 && lane == 0 && ti < 64) a.timeline[ti * 8 + 2] = clock64();
+        u = nu;
+        kt = nkt;
+        kt1 = nkt1;
+        slot_cur = slot_nxt;
+        have_cur = have_nxt;
+        have_nxt = false;
+        ++ti;
       }
     }
     __syncwarp();
@@ -300,208 +420,240 @@ absorb_attn_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const int key_l = ab_key_of_lane(q, lane);
     const bool lane_ok = ab_lane_valid(lane);
     // byte offset of this key's element in row h of P^T: h * 128 + (((key >> 3) ^ (h & 7)) << 4) + (key & 7) * 2
-    unsigned char* p_col = sP + (key_l & 7) * 2;
+    unsigned char* p_col0 = sP + (key_l & 7) * 2;
     const int key_piece = key_l >> 3;
+    const uint32_t peer_e = ab_mapa(smem_u32(sE), peer), peer_ebar = ab_mapa(smem_u32(e_full), peer);
     float m_run[kAbMaxHeads], l_part[kAbMaxHeads];
-    uint32_t sph = 0, odph = 0;
-    for (int t = lo; t < hi; ++t) {
-      const int w = t / tpw, kt = t - w * tpw;
-      const bool seg_first = (t == lo) || (kt == 0);
-      const bool seg_last = (t + 1 == hi) || (kt + 1 == tpw);
-      if (seg_first) {
+    uint32_t odph = 0;
+    int ti = 0;
+    for (int u = cl; u < n_units; u += G) {
+      const int w = u / nsplit, chunk = u - w * nsplit;
+      const int kt0 = chunk * tpc, kt1 = min(tpw, kt0 + tpc);
+      for (int kt = kt0; kt < kt1; ++kt, ++ti) {
+        const bool seg_first = kt == kt0, seg_last = kt + 1 == kt1;
+        const int sb = ti & 1;
+        const uint32_t par = (ti >> 1) & 1;
+        if (seg_first) {
 #pragma unroll
-        for (int h = 0; h < kAbMaxHeads; ++h) {
-          m_run[h] = -INFINITY;
-          l_part[h] = 0.0f;
-        }
-      }
-      const bool tl = a.timeline && cta == 0 && gt == 0 && t - lo < 64;
-      mbar_wait(s_full, sph);
-      sph ^= 1;
-      tcgen05_fence_after();
-      if (tl) a.timeline[(t - lo) * 8 + 3] = clock64();
-      uint32_t r[32];
-      tmem_ld_32x32(t_lane + kAbSCol, r);
-      tmem_wait_ld();
-      const bool valid = lane_ok && (kt * kAbKeys + key_l < T);
-      float s[kAbMaxHeads];
-      float over = -INFINITY;  // how far this key's scores exceed the running maxima
-#pragma unroll
-      for (int h = 0; h < kAbMaxHeads; ++h) {
-        s[h] = valid ? __uint_as_float(r[h]) * a.scale : -INFINITY;
-        if (h < H) over = fmaxf(over, s[h] - m_run[h]);
-      }
-      // Fast path (every tile but a window's first few): no score exceeds its head's running maximum by more than 2^8,
-      // the probabilities are taken against the (lagging) running maxima -- one barrier with an OR instead of 20 maxima.
-      if (ab_group_or(over > 8.0f)) {
-#pragma unroll
-        for (int h = 0; h < kAbMaxHeads; ++h) {
-          const int wm = __reduce_max_sync(0xffffffffu, ab_ord(s[h]));
-          if (lane == h) s_wmax[h * 4 + q] = ab_unord(wm);
-        }
-        ab_group_sync();
-        float alpha[kAbMaxHeads];
-#pragma unroll
-        for (int h = 0; h < kAbMaxHeads; ++h) {
-          const float4 v = *reinterpret_cast<const float4*>(s_wmax + h * 4);
-          const float m_new = fmaxf(m_run[h], fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-          alpha[h] = ab_exp2(m_run[h] - m_new);  // 0 on a window's first tile (m_run = -inf)
-          m_run[h] = m_new;
-          l_part[h] *= alpha[h];
-        }
-        if (!seg_first) {  // rescale O' (tensor memory); the previous tile's output MMAs completed before S arrived
-          for (int j = 0; j < n_dblk; ++j) {
-            uint32_t o[32];
-            tmem_ld_32x32(t_lane + kAbOCol + j * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int h = 0; h < kAbMaxHeads; ++h) o[h] = __float_as_uint(__uint_as_float(o[h]) * alpha[h]);
-            tmem_st_32x32(t_lane + kAbOCol + j * 32, o);
+          for (int h = 0; h < kAbMaxHeads; ++h) {
+            m_run[h] = -INFINITY;
+            l_part[h] = 0.0f;
           }
-          tmem_wait_st();
         }
-        ab_group_sync();  // s_wmax may be rewritten by the next slow tile
-      }
-      if (tl) a.timeline[(t - lo) * 8 + 4] = clock64();
-      // probabilities (allowed to reach 2^8: harmless in bf16 / fp32) -> P^T rows (heads), K-major over this tile's keys
+        const bool tl = a.timeline && blockIdx.x == 0 && gt == 0 && ti < 64;
+        mbar_wait(&s_full[sb], par);
+        tcgen05_fence_after();
+        if (tl) a.timeline[ti * 8 + 3] = clock64();
+        uint32_t r[32];
+        tmem_ld_32x32(t_lane + kAbSCol + sb * 32, r);
+        tmem_wait_ld();
+        // this CTA's partial scores -> the peer's exchange buffer; the peer's arrive in ours
+        if (lane_ok) {
+          const uint32_t dst = peer_e + (uint32_t)((sb * kAbKeys + key_l) * kAbMaxHeads) * 4u;
 #pragma unroll
-      for (int h = 0; h < kAbMaxHeads; ++h) {
-        const float p = ab_exp2(s[h] - m_run[h]);  // 0 for masked keys
-        l_part[h] += p;
-        if (lane_ok && h < H)
-          *reinterpret_cast<__nv_bfloat16*>(p_col + h * 128 + ((key_piece ^ (h & 7)) << 4)) = __float2bfloat16(p);
-      }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      mbar_arrive(p_full);
-      if (tl) a.timeline[(t - lo) * 8 + 5] = clock64();
-
-      if (seg_last) {
-        // ---- flush this CTA's part of window w: (max, sum, O') -> partial slot; the last CTA of the window merges ----
-        const int b = s_act[w];
-        const int slot_id = cta * kAbWinPerCta + (w - w_first);
+          for (int h4 = 0; h4 < kAbMaxHeads / 4; ++h4)
+            ab_st_remote_v4(dst + h4 * 16, make_float4(__uint_as_float(r[4 * h4]), __uint_as_float(r[4 * h4 + 1]),
+                                                       __uint_as_float(r[4 * h4 + 2]), __uint_as_float(r[4 * h4 + 3])));
+        }
+        ab_group_sync();  // all partial scores of this CTA are stored: one release-arrive on the peer's barrier
+        if (gt == 0) ab_arrive_remote(peer_ebar + sb * 8);
+        if (lane == 0) ab_wait_cluster(&e_full[sb], par);
+        __syncwarp();
+        const bool valid = lane_ok && (kt * kAbKeys + key_l < T);
+        float s[kAbMaxHeads];
+        float over = -INFINITY;  // how far this key's scores exceed the running maxima
+        {
+          const float4* pe = reinterpret_cast<const float4*>(sE + (sb * kAbKeys + (lane_ok ? key_l : 0)) * kAbMaxHeads);
+#pragma unroll
+          for (int h4 = 0; h4 < kAbMaxHeads / 4; ++h4) {
+            const float4 v = pe[h4];
+            s[4 * h4 + 0] = __uint_as_float(r[4 * h4 + 0]) + v.x;
+            s[4 * h4 + 1] = __uint_as_float(r[4 * h4 + 1]) + v.y;
+            s[4 * h4 + 2] = __uint_as_float(r[4 * h4 + 2]) + v.z;
+            s[4 * h4 + 3] = __uint_as_float(r[4 * h4 + 3]) + v.w;
+          }
+        }
 #pragma unroll
         for (int h = 0; h < kAbMaxHeads; ++h) {
-          const float v = warp_sum(l_part[h]);
-          if (lane == 0) s_lsum[q * kAbMaxHeads + h] = v;
+          s[h] = valid ? s[h] * a.scale : -INFINITY;
+          if (h < H) over = fmaxf(over, s[h] - m_run[h]);
         }
-        // contributors of window w: the CTAs whose (non-empty) tile range meets [w * tpw, (w + 1) * tpw); their partial
-        // slots go to s_sid (warp 4 tests one candidate CTA per lane)
-        const long long wlo = (long long)w * tpw, whi = wlo + tpw;
-        if (q == 0) {
-          const int c_first = (int)(((wlo + 1) * G - 1) / total), c_last = (int)((whi * G - 1) / total);
-          const int c2 = c_first + lane;
-          const long long l2 = ((long long)c2 * total) / G, h2 = ((long long)(c2 + 1) * total) / G;
-          const bool on = c2 <= c_last && h2 > l2 && l2 < whi && h2 > wlo;
-          const unsigned int mk = __ballot_sync(0xffffffffu, on);
-          if (on) s_sid[__popc(mk & ((1u << lane) - 1))] = c2 * kAbWinPerCta + (w - (int)(l2 / tpw));
-          if (lane == 0) *s_ncontrib = __popc(mk);
-        }
-        mbar_wait(o_done, odph);
-        odph ^= 1;
-        tcgen05_fence_after();
-        float* dst = a.part + (long long)slot_id * H * d;
-        for (int j = 0; j < n_dblk; ++j) {
-          uint32_t o[32];
-          tmem_ld_32x32(t_lane + kAbOCol + j * 32, o);
-          tmem_wait_ld();
-          const int dim = j * 128 + q * 32 + lane;
+        // Fast path (every tile but a unit's first few): no score exceeds its head's running maximum by more than 2^8,
+        // the probabilities are taken against the (lagging) running maxima -- one barrier with an OR instead of 20 maxima.
+        if (ab_group_or(over > 8.0f)) {
 #pragma unroll
-          for (int h = 0; h < kAbMaxHeads; ++h)
-            if (h < H) dst[(long long)h * d + dim] = __uint_as_float(o[h]);
-        }
-        tcgen05_fence_before();
-        mbar_arrive(o_free);
-        ab_group_sync();  // s_lsum / s_sid complete
-        if (gt < H) {
-          float* ml = a.part_ml + (long long)slot_id * 2 * kAbMaxHeads;
-          float mv = 0.0f;
-#pragma unroll
-          for (int h = 0; h < kAbMaxHeads; ++h)
-            if (h == gt) mv = m_run[h];
-          ml[gt] = mv;
-          ml[kAbMaxHeads + gt] = (s_lsum[gt] + s_lsum[kAbMaxHeads + gt]) + (s_lsum[2 * kAbMaxHeads + gt] + s_lsum[3 * kAbMaxHeads + gt]);
-        }
-        const int n_contrib = *s_ncontrib;
-        __threadfence();
-        ab_group_sync();
-        if (gt == 0) *s_last = (atomicAdd(a.cnt + b, 1) == n_contrib - 1) ? 1 : 0;
-        ab_group_sync();
-        if (*s_last) {
-          __threadfence();
-          // weights of the contributors: w_c[h] = 2^(m_c[h] - max_c m_c[h]) / sum_c l_c[h] 2^(m_c[h] - max)
-          if (gt < H) {
-            float M = -INFINITY;
-            for (int k2 = 0; k2 < n_contrib; ++k2) M = fmaxf(M, __ldcg(a.part_ml + (long long)s_sid[k2] * 2 * kAbMaxHeads + gt));
-            float L = 0.0f;
-            for (int k2 = 0; k2 < n_contrib; ++k2) {
-              const float* ml = a.part_ml + (long long)s_sid[k2] * 2 * kAbMaxHeads;
-              const float wc = ab_exp2(__ldcg(ml + gt) - M);
-              L = fmaf(__ldcg(ml + kAbMaxHeads + gt), wc, L);
-              s_w[k2 * kAbMaxHeads + gt] = wc;
-            }
-            const float linv = 1.0f / L;
-            for (int k2 = 0; k2 < n_contrib; ++k2) s_w[k2 * kAbMaxHeads + gt] *= linv;
+          for (int h = 0; h < kAbMaxHeads; ++h) {
+            const int wm = __reduce_max_sync(0xffffffffu, ab_ord(s[h]));
+            if (lane == h) s_wmax[h * 4 + q] = ab_unord(wm);
           }
           ab_group_sync();
-          __nv_bfloat16* o = a.out + (long long)b * H * d;
-          const int n4 = H * d / 4;  // float4 columns of the (n_head, d) tile; thread gt takes gt, gt + 128, ...
-          if (n_contrib <= 3) {      // the common case: up to three contributors, all loads of four columns in flight
-            const float* p0 = a.part + (long long)s_sid[0] * H * d;
-            const float* p1 = a.part + (long long)s_sid[n_contrib > 1 ? 1 : 0] * H * d;
-            const float* p2 = a.part + (long long)s_sid[n_contrib > 2 ? 2 : 0] * H * d;
-            for (int i4 = gt; i4 < n4; i4 += 128 * 4) {
-              float4 v0[4], v1[4], v2[4];
+          float alpha[kAbMaxHeads];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int i = min(i4 + u * 128, n4 - 1);
-                v0[u] = __ldcg(reinterpret_cast<const float4*>(p0) + i);
-                v1[u] = __ldcg(reinterpret_cast<const float4*>(p1) + i);
-                v2[u] = __ldcg(reinterpret_cast<const float4*>(p2) + i);
-              }
+          for (int h = 0; h < kAbMaxHeads; ++h) {
+            const float4 v = *reinterpret_cast<const float4*>(s_wmax + h * 4);
+            const float m_new = fmaxf(m_run[h], fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+            alpha[h] = ab_exp2(m_run[h] - m_new);  // 0 on a unit's first tile (m_run = -inf)
+            m_run[h] = m_new;
+            l_part[h] *= alpha[h];
+          }
+          if (!seg_first) {
+            // rescale O' (tensor memory).  The scores of this tile were issued BEFORE the output MMAs of the previous
+            // one, so their arrival says nothing about those: wait for the previous tile's o_sync phase (the output MMAs
+            // of this tile cannot start before the p_full arrive below, so that phase is the latest one).
+            mbar_wait(o_sync, (uint32_t)((ti - 1) & 1));
+            tcgen05_fence_after();
+            for (int j = 0; j < n_dblk; ++j) {
+              uint32_t o[32];
+              tmem_ld_32x32(t_lane + kAbOCol + j * 32, o);
+              tmem_wait_ld();
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int i = i4 + u * 128;
-                if (i < n4) {
-                  const int h = (i * 4) / d;
-                  const float w0 = s_w[h], w1 = n_contrib > 1 ? s_w[kAbMaxHeads + h] : 0.0f,
-                              w2 = n_contrib > 2 ? s_w[2 * kAbMaxHeads + h] : 0.0f;
-                  const float ox = fmaf(v2[u].x, w2, fmaf(v1[u].x, w1, v0[u].x * w0));
-                  const float oy = fmaf(v2[u].y, w2, fmaf(v1[u].y, w1, v0[u].y * w0));
-                  const float oz = fmaf(v2[u].z, w2, fmaf(v1[u].z, w1, v0[u].z * w0));
-                  const float ow = fmaf(v2[u].w, w2, fmaf(v1[u].w, w1, v0[u].w * w0));
-                  reinterpret_cast<uint2*>(o)[i] = make_uint2(pack_bf16x2(ox, oy), pack_bf16x2(oz, ow));
-                }
-              }
+              for (int h = 0; h < kAbMaxHeads; ++h) o[h] = __float_as_uint(__uint_as_float(o[h]) * alpha[h]);
+              tmem_st_32x32(t_lane + kAbOCol + j * 32, o);
             }
+            tmem_wait_st();
+          }
+          ab_group_sync();  // s_wmax may be rewritten by the next slow tile
+        }
+        if (tl) a.timeline[ti * 8 + 4] = clock64();
+        // probabilities (allowed to reach 2^8: harmless in bf16 / fp32) -> P^T rows (heads), K-major over this tile's keys
+        // (two P buffers: the output MMAs of the previous tile may still be reading theirs)
+        unsigned char* p_col = p_col0 + sb * kAbPBytes;
+#pragma unroll
+        for (int h = 0; h < kAbMaxHeads; ++h) {
+          const float p = ab_exp2(s[h] - m_run[h]);  // 0 for masked keys
+          l_part[h] += p;
+          if (lane_ok && h < H)
+            *reinterpret_cast<__nv_bfloat16*>(p_col + h * 128 + ((key_piece ^ (h & 7)) << 4)) = __float2bfloat16(p);
+        }
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        mbar_arrive(p_full);
+        if (tl) a.timeline[ti * 8 + 5] = clock64();
+
+        if (seg_last) {
+          const int b = s_act[w];
+#pragma unroll
+          for (int h = 0; h < kAbMaxHeads; ++h) {
+            const float v = warp_sum(l_part[h]);
+            if (lane == 0) s_lsum[q * kAbMaxHeads + h] = v;
+          }
+          ab_group_sync();
+          float l_tot[kAbMaxHeads];
+#pragma unroll
+          for (int h = 0; h < kAbMaxHeads; ++h)
+            l_tot[h] = (s_lsum[h] + s_lsum[kAbMaxHeads + h]) + (s_lsum[2 * kAbMaxHeads + h] + s_lsum[3 * kAbMaxHeads + h]);
+          mbar_wait(o_done, odph);
+          odph ^= 1;
+          tcgen05_fence_after();
+          if (nsplit == 1) {
+            // ---- the unit is the whole window: normalise and store this CTA's features of sum_t p xa_t ----
+            __nv_bfloat16* o = a.out + (long long)b * H * d + f0;
+#pragma unroll
+            for (int h = 0; h < kAbMaxHeads; ++h) l_tot[h] = 1.0f / l_tot[h];
+            for (int j = 0; j < n_dblk; ++j) {
+              uint32_t v[32];
+              tmem_ld_32x32(t_lane + kAbOCol + j * 32, v);
+              tmem_wait_ld();
+              const int dim = j * 128 + q * 32 + lane;
+#pragma unroll
+              for (int h = 0; h < kAbMaxHeads; ++h)
+                if (h < H) o[(long long)h * d + dim] = __float2bfloat16(__uint_as_float(v[h]) * l_tot[h]);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(o_free);
           } else {
-            for (int i = gt; i < n4; i += 128) {
-              const int h = (i * 4) / d;
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-              for (int k2 = 0; k2 < n_contrib; ++k2) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(a.part + (long long)s_sid[k2] * H * d) + i);
-                const float wc = s_w[k2 * kAbMaxHeads + h];
-                acc.x = fmaf(v.x, wc, acc.x);
-                acc.y = fmaf(v.y, wc, acc.y);
-                acc.z = fmaf(v.z, wc, acc.z);
-                acc.w = fmaf(v.w, wc, acc.w);
-              }
-              reinterpret_cast<uint2*>(o)[i] = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+            // ---- (max, sum, O') of this chunk -> partial slot (sequence, chunk), [feature][head]; absorb_merge_kernel
+            //      combines the chunks of a window ----
+            const int slot_id = b * nsplit + chunk;
+            float* dst = a.part + ((long long)slot_id * d + f0) * kAbMaxHeads;
+            for (int j = 0; j < n_dblk; ++j) {
+              uint32_t v[32];
+              tmem_ld_32x32(t_lane + kAbOCol + j * 32, v);
+              tmem_wait_ld();
+              float4* o4 = reinterpret_cast<float4*>(dst + (long long)(j * 128 + q * 32 + lane) * kAbMaxHeads);
+#pragma unroll
+              for (int h4 = 0; h4 < kAbMaxHeads / 4; ++h4)
+                o4[h4] = make_float4(__uint_as_float(v[4 * h4]), __uint_as_float(v[4 * h4 + 1]), __uint_as_float(v[4 * h4 + 2]),
+                                     __uint_as_float(v[4 * h4 + 3]));
+            }
+            tcgen05_fence_before();
+            mbar_arrive(o_free);
+            if (rank == 0 && gt < kAbMaxHeads) {  // (both CTAs of the pair hold the same values)
+              float* ml = a.part_ml + (long long)slot_id * 2 * kAbMaxHeads;
+              float mv = 0.0f, lv = 0.0f;
+#pragma unroll
+              for (int h = 0; h < kAbMaxHeads; ++h)
+                if (h == gt) {
+                  mv = m_run[h];
+                  lv = l_tot[h];
+                }
+              ml[gt] = mv;
+              ml[kAbMaxHeads + gt] = lv;
             }
           }
-          if (gt == 0) a.cnt[b] = 0;  // ready for the next launch
+          ab_group_sync();  // s_lsum is reused by the next unit
+          if (tl) a.timeline[ti * 8 + 6] = clock64();
         }
-        ab_group_sync();  // s_last / s_w / s_sid / s_lsum are reused by the next window
-        if (tl) a.timeline[(t - lo) * 8 + 6] = clock64();
       }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  ab_cluster_sync();  // nobody exits while the peer may still write its partial scores here or signal these barriers
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kAbTmemCols);
+  }
+}
+
+// Combines the chunks of every live window (nsplit > 1): out[b][h][:] = sum_c w_c[h] O'_c[:][h], w_c[h] =
+// 2^(m_c[h] - max_c m_c[h]) / sum_c l_c[h] 2^(m_c[h] - max).  CTA = (sequence, 64-feature block): the [feature][head]
+// partial rows are read as they lie and transposed to [head][feature] through shared memory.
+constexpr int kMgThreads = 256;
+constexpr int kMgDims = 64;
+__global__ void __launch_bounds__(kMgThreads)
+absorb_merge_kernel(const float* __restrict__ part, const float* __restrict__ part_ml, const int* __restrict__ finished,
+                    int n_head, int d, int nsplit, __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_w[kAbMaxContrib][kAbMaxHeads];
+  __shared__ float s_o[kMgDims][kAbMaxHeads + 1];
+  const int b = blockIdx.y, d0 = blockIdx.x * kMgDims, tid = threadIdx.x;
+  if (finished != nullptr && finished[b]) return;
+  if (tid < kAbMaxHeads) {
+    const float* ml = part_ml + (long long)b * nsplit * 2 * kAbMaxHeads;
+    float M = -INFINITY;
+    for (int c = 0; c < nsplit; ++c) M = fmaxf(M, ml[c * 2 * kAbMaxHeads + tid]);
+    float L = 0.0f;
+    for (int c = 0; c < nsplit; ++c) {
+      const float wc = ab_exp2(ml[c * 2 * kAbMaxHeads + tid] - M);
+      L = fmaf(ml[c * 2 * kAbMaxHeads + kAbMaxHeads + tid], wc, L);
+      s_w[c][tid] = wc;
+    }
+    const float linv = 1.0f / L;
+    for (int c = 0; c < nsplit; ++c) s_w[c][tid] *= linv;
+  }
+  __syncthreads();
+  // 64 features x 20 heads = 320 float4 per chunk: thread -> (feature, head quad)
+  constexpr int kQuads = kAbMaxHeads / 4;
+  for (int i = tid; i < kMgDims * kQuads; i += kMgThreads) {
+    const int f = i / kQuads, hq = i - f * kQuads;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < nsplit; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(part + (((long long)b * nsplit + c) * d + d0 + f) * kAbMaxHeads + hq * 4);
+      acc.x = fmaf(v.x, s_w[c][hq * 4 + 0], acc.x);
+      acc.y = fmaf(v.y, s_w[c][hq * 4 + 1], acc.y);
+      acc.z = fmaf(v.z, s_w[c][hq * 4 + 2], acc.z);
+      acc.w = fmaf(v.w, s_w[c][hq * 4 + 3], acc.w);
+    }
+    s_o[f][hq * 4 + 0] = acc.x;
+    s_o[f][hq * 4 + 1] = acc.y;
+    s_o[f][hq * 4 + 2] = acc.z;
+    s_o[f][hq * 4 + 3] = acc.w;
+  }
+  __syncthreads();
+  for (int i = tid; i < n_head * (kMgDims / 2); i += kMgThreads) {
+    const int h = i / (kMgDims / 2), f2 = (i - h * (kMgDims / 2)) * 2;
+    *reinterpret_cast<uint32_t*>(out + ((long long)b * n_head + h) * d + d0 + f2) = pack_bf16x2(s_o[f2][h], s_o[f2 + 1][h]);
   }
 }
 
@@ -555,32 +707,46 @@ absorb_q_kernel(const __grid_constant__ CUtensorMap tm_wk, const __grid_constant
     tmem_alloc(tmem_slot, kQaIb * 64);
     tmem_relinquish();
   } else {
-    // A tile: thread covers 4 consecutive columns of rows (tid / 16) + 8 * it; 16-byte pieces XOR-swizzled with row % 8
+    // A tile: thread covers 4 consecutive columns of rows (tid / 16) + 8 * it; 16-byte pieces XOR-swizzled with row % 8.
+    // The slab loads of four row groups (up to 32 x 16 bytes per thread) are issued before any of them is used.
     const int c4 = (tid & 15) * 4, r0 = tid >> 4;
-    const float4 bias = a.part ? *reinterpret_cast<const float4*>(a.bias + h * 64 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-      const int r = r0 + 8 * it, row = row0 + r;
-      uint2 packed = make_uint2(0, 0);
-      if (row < a.rows) {
-        if (a.part) {
-          float4 v = bias;
-          float4 pp[8];
-#pragma unroll
-          for (int s2 = 0; s2 < 8; ++s2)
-            pp[s2] = s2 < a.n_split ? *reinterpret_cast<const float4*>(a.part + s2 * a.split_stride + (long long)row * d + h * 64 + c4)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int s2 = 0; s2 < 8; ++s2) {
-            v.x += pp[s2].x; v.y += pp[s2].y; v.z += pp[s2].z; v.w += pp[s2].w;
-          }
-          packed = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-        } else {
-          packed = *reinterpret_cast<const uint2*>(a.q + (long long)row * d + h * 64 + c4);
-        }
-      }
+    auto put = [&](int r, uint2 packed) {
       const int piece = (c4 >> 3) ^ (r & 7);
       *reinterpret_cast<uint2*>(sA + r * 128 + piece * 16 + (c4 & 7) * 2) = packed;
+    };
+    if (a.part) {
+      const float4 bias = *reinterpret_cast<const float4*>(a.bias + h * 64 + c4);
+      const float* base = a.part + (long long)row0 * d + h * 64 + c4;
+      const int ns = a.n_split;
+#pragma unroll 1
+      for (int it0 = 0; it0 < 16; it0 += 4) {
+        float4 pp[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + 8 * (it0 + u);
+          const bool on = row0 + r < a.rows;
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2)
+            pp[u][s2] = (on && s2 < ns) ? __ldcg(reinterpret_cast<const float4*>(base + s2 * a.split_stride + (long long)r * d))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + 8 * (it0 + u);
+          float4 v = bias;
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2) {
+            v.x += pp[u][s2].x; v.y += pp[u][s2].y; v.z += pp[u][s2].z; v.w += pp[u][s2].w;
+          }
+          put(r, row0 + r < a.rows ? make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)) : make_uint2(0, 0));
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {
+        const int r = r0 + 8 * it;
+        put(r, row0 + r < a.rows ? *reinterpret_cast<const uint2*>(a.q + (long long)(row0 + r) * d + h * 64 + c4) : make_uint2(0, 0));
+      }
     }
     fence_proxy_async_smem();
   }
@@ -634,10 +800,12 @@ absorb_q_kernel(const __grid_constant__ CUtensorMap tm_wk, const __grid_constant
 
 // =============================================================================================== K14c
 // att[b][h*64 + j] = Wv[h*64 + j] . O'[b][h] + bv[h*64 + j]: per head a (rows x d) x (d x 64) GEMM whose A operand is
-// that head's slice of the merged attention output.  CTA = (32-column tile, 128-row tile), K = d in 64-wide blocks.
+// that head's slice of the merged attention output.  CTA = (16-column tile, 128-row tile), K = d in 64-wide blocks
+// through an 8-stage TMA ring (80 CTAs for d = 1280: the kernel is a latency chain, not work).
 constexpr int kVoThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM, warps 2-5 epilogue
-constexpr int kVoStages = 4;
-constexpr int kVoABytes = 128 * 128, kVoBBytes = 32 * 128;
+constexpr int kVoStages = 8;
+constexpr int kVoBN = 16;
+constexpr int kVoABytes = 128 * 128, kVoBBytes = kVoBN * 128;
 constexpr int kVoStageBytes = kVoABytes + kVoBBytes;
 constexpr int kVoSmem = kVoStages * kVoStageBytes + 256 + 1024;
 
@@ -653,7 +821,7 @@ absorb_v_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dfull + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nt = blockIdx.x, row0 = blockIdx.y * 128;
-  const int head = nt >> 1, num_kb = d / 64;
+  const int head = (nt * kVoBN) >> 6, num_kb = d / 64;
   if (tid == 0) {
     tma_prefetch_desc(&tm_o);
     tma_prefetch_desc(&tm_wv);
@@ -681,7 +849,7 @@ absorb_v_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
         mbar_wait(&empty[st], ph ^ 1);
         mbar_expect_tx(&full[st], kVoStageBytes);
         tma_load_3d(smem + st * kVoStageBytes, &tm_o, &full[st], head * d + kb * 64, row0, 0);
-        tma_load_3d(smem + st * kVoStageBytes + kVoABytes, &tm_wv, &full[st], kb * 64, nt * 32, 0);
+        tma_load_3d(smem + st * kVoStageBytes + kVoABytes, &tm_wv, &full[st], kb * 64, nt * kVoBN, 0);
         if (++st == kVoStages) {
           st = 0;
           ph ^= 1;
@@ -690,7 +858,7 @@ absorb_v_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
     }
     __syncwarp();
   } else if (uwarp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, 32, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(128, kVoBN, 0, 0);
     int st = 0;
     uint32_t ph = 0;
     const uint32_t s_base = smem_u32(smem);
@@ -717,11 +885,11 @@ absorb_v_kernel(const __grid_constant__ CUtensorMap tm_o, const __grid_constant_
     uint32_t r[32];
     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), r);
     tmem_wait_ld();
-    if (row < rows) {
-      const float* bp = bias + nt * 32;
-      uint4* dst = reinterpret_cast<uint4*>(att + (long long)row * d + nt * 32);
+    if (row < rows) {  // (the accumulator is 16 columns wide; the upper half of the 32-column load is ignored)
+      const float* bp = bias + nt * kVoBN;
+      uint4* dst = reinterpret_cast<uint4*>(att + (long long)row * d + nt * kVoBN);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kVoBN / 8; ++k) {
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * k + e]) + __ldg(bp + 8 * k + e);
@@ -905,20 +1073,41 @@ int init_absorb() {
 }
 
 bool absorb_applicable(int n_seq, int n_head, int d, int T) {
-  return n_seq >= 1 && n_seq <= kAbMaxSeq && n_head <= kAbMaxHeads && n_head * 64 == d && d % 128 == 0 &&
-         d / 128 <= kAbMaxDblk && T >= 1 && (T + kAbKeys - 1) / kAbKeys <= 24;
+  return n_seq >= 1 && n_seq <= kAbMaxSeq && n_head <= kAbMaxHeads && n_head * 64 == d && d % 256 == 0 &&
+         d / 256 <= kAbMaxDblk && T >= 1 && (T + kAbKeys - 1) / kAbKeys <= 2 * kAbMaxContrib && (device_sm_count() & 1) == 0;
+}
+
+// Chunks per window: the smallest split whose units fill the CTA-pair rounds nearly as well as the best split does
+// (a window alone is one unit; 120 windows on 74 pairs would leave the second round 38 % empty).  A function of
+// (n_seq, T) only, so that a window's result does not depend on what else is in the batch.
+int absorb_nsplit(int n_seq, int T) {
+  const int tpw = (T + kAbKeys - 1) / kAbKeys, G = device_sm_count() / 2;
+  double fill[kAbMaxContrib + 1];
+  double best = 0.0;
+  int last = 0;
+  for (int ns = 1; ns <= kAbMaxContrib; ++ns) {
+    const int tpc = (tpw + ns - 1) / ns, eff = (tpw + tpc - 1) / tpc;
+    fill[ns] = 0.0;
+    if (eff != ns || (ns > 1 && (tpc < 2 || n_seq * ns > kAbMaxUnits))) continue;  // (not a distinct / allowed split)
+    const int units = n_seq * ns, rounds = (units + G - 1) / G;
+    fill[ns] = (double)units / ((double)rounds * G);
+    if (fill[ns] > best) best = fill[ns];
+    last = ns;
+  }
+  for (int ns = 1; ns <= last; ++ns)
+    if (fill[ns] >= 0.93 * best) return ns;
+  return 1;
 }
 
 size_t absorb_workspace_bytes(int n_seq, int n_head, int d) {
   const size_t rows = ((size_t)n_seq + 127) / 128 * 128;
-  const size_t G = (size_t)device_sm_count();
   size_t b = 0;
   auto add = [&](size_t x) { b += (x + 1023) / 1024 * 1024; };
   add(rows * kAbQRows * d * 2);                        // qa
   add(rows * n_head * d * 2);                          // merged O'
-  add(G * kAbWinPerCta * n_head * d * 4);              // partial O'
-  add(G * kAbWinPerCta * 2 * kAbMaxHeads * 4);         // partial (max, sum)
-  add(kAbMaxSeq * 4);                                  // arrival counters
+  add((size_t)kAbMaxUnits * d * kAbMaxHeads * 4);      // partial O' ([feature][kAbMaxHeads] per slot)
+  add((size_t)kAbMaxUnits * 2 * kAbMaxHeads * 4);      // partial (max, sum)
+  add(2 * kAbMaxSeq * 4);                              // arrival counters (per feature half)
   return b;
 }
 
@@ -931,7 +1120,6 @@ struct AbsorbWs {
 };
 static AbsorbWs carve_absorb(void* ws, int n_seq, int n_head, int d) {
   const size_t rows = ((size_t)n_seq + 127) / 128 * 128;
-  const size_t G = (size_t)device_sm_count();
   unsigned char* p = static_cast<unsigned char*>(ws);
   auto take = [&](size_t x) {
     void* r = p;
@@ -941,9 +1129,9 @@ static AbsorbWs carve_absorb(void* ws, int n_seq, int n_head, int d) {
   AbsorbWs o;
   o.qa = static_cast<__nv_bfloat16*>(take(rows * kAbQRows * d * 2));
   o.merged = static_cast<__nv_bfloat16*>(take(rows * n_head * d * 2));
-  o.part = static_cast<float*>(take(G * kAbWinPerCta * n_head * d * 4));
-  o.part_ml = static_cast<float*>(take(G * kAbWinPerCta * 2 * kAbMaxHeads * 4));
-  o.cnt = static_cast<int*>(take(kAbMaxSeq * 4));
+  o.part = static_cast<float*>(take((size_t)kAbMaxUnits * d * kAbMaxHeads * 4));
+  o.part_ml = static_cast<float*>(take((size_t)kAbMaxUnits * 2 * kAbMaxHeads * 4));
+  o.cnt = static_cast<int*>(take(2 * kAbMaxSeq * 4));
   return o;
 }
 
@@ -952,7 +1140,7 @@ int absorb_prepare(void* ws, int n_seq, int n_head, int d, cudaStream_t stream) 
   const size_t rows = ((size_t)n_seq + 127) / 128 * 128;
   B200W_CUDA_OK(cudaMemsetAsync(w.qa, 0, rows * kAbQRows * d * 2, stream));
   B200W_CUDA_OK(cudaMemsetAsync(w.merged, 0, rows * n_head * d * 2, stream));
-  B200W_CUDA_OK(cudaMemsetAsync(w.cnt, 0, kAbMaxSeq * 4, stream));
+  B200W_CUDA_OK(cudaMemsetAsync(w.cnt, 0, 2 * kAbMaxSeq * 4, stream));
   return kOk;
 }
 
@@ -1009,17 +1197,37 @@ int launch_absorbed_cross_attention(const float* q_part, int n_split, long long 
     aa.cnt = w.cnt;
     aa.out = w.merged;
     aa.scale = 0.125f * kAbLog2e;
+    aa.nsplit = absorb_nsplit(n_seq, T);
     aa.timeline = g_absorb_timeline;
     ProfScope prof_("absorb_attn", stream);
-    B200W_CUDA_OK(launch_k(absorb_attn_kernel, dim3(device_sm_count()), dim3(kAbThreads), kAbSmemBytes, stream, tx, tq, aa));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(device_sm_count() & ~1);
+    cfg.blockDim = dim3(kAbThreads);
+    cfg.dynamicSmemBytes = kAbSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;  // CTA pairs: each CTA holds half of the features of a key tile
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200W_CUDA_OK(cudaLaunchKernelEx(&cfg, absorb_attn_kernel, tx, tq, aa));
     count_launch();
+    if (aa.nsplit > 1) {
+      ProfScope prof2_("absorb_merge", stream);
+      B200W_CUDA_OK(launch_k(absorb_merge_kernel, dim3(d / kMgDims, n_seq), dim3(kMgThreads), 0, stream,
+                             static_cast<const float*>(w.part), static_cast<const float*>(w.part_ml), finished, n_head, d,
+                             aa.nsplit, w.merged));
+      count_launch();
+    }
   }
   {  // K14c
     CUtensorMap to, twv;
     B200W_TRY(make_tmap_a(&to, w.merged, 1, n_seq, n_head * d, (long long)n_head * d, (long long)n_seq * n_head * d));
-    B200W_TRY(make_tmap_w(&twv, static_cast<const __nv_bfloat16*>(w_ckv) + (size_t)d * d, d, d, 32));
+    B200W_TRY(make_tmap_w(&twv, static_cast<const __nv_bfloat16*>(w_ckv) + (size_t)d * d, d, d, kVoBN));
     ProfScope prof_("absorb_v", stream);
-    B200W_CUDA_OK(launch_k(absorb_v_kernel, dim3(d / 32, tiles_m), dim3(kVoThreads), kVoSmem, stream, to, twv, n_seq, d,
+    B200W_CUDA_OK(launch_k(absorb_v_kernel, dim3(d / kVoBN, tiles_m), dim3(kVoThreads), kVoSmem, stream, to, twv, n_seq, d,
                            b_ckv + d, att));
     count_launch();
   }
