@@ -68,11 +68,15 @@ bool pdl_enabled() {
   return v != 0;
 }
 
-// B200W_SMALL=0 keeps batches of <= 5 sequences on the chain / per-phase path instead of the one-launch step (K13)
+// The one-launch step (K13) is taken for batches of <= 3 sequences: measured on B200 (large-v3) 1.37 / 1.79 / 2.40 / 3.55 /
+// 4.15 ms per step at 1 .. 5 sequences against 2.59 / 2.44 / 2.71 / 2.77 / 2.72 ms on the chain path.  B200W_SMALL=0 keeps
+// every batch on the chain path, B200W_SMALL=1 takes K13 wherever it applies (<= 5 sequences).
 // (read on every call, not cached: the parity tests switch between the two paths inside one process)
-static bool small_enabled() {
+static bool small_enabled(int n_seq) {
   const char* e = getenv("B200W_SMALL");
-  return !(e != nullptr && e[0] == '0');
+  if (e != nullptr && e[0] == '0') return false;
+  if (e != nullptr && e[0] == '1') return true;
+  return n_seq <= 3;
 }
 
 // B200W_ABSORB=1: single-token steps of batches >= kAbsorbMinBatch run the cross-attention in absorbed form (K14)
@@ -727,7 +731,7 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   float* kvp = ca_split ? bf.ca_part : nullptr;
   int* kvc = ca_split ? bf.ca_cnt : nullptr;
   if (ca_split) B200W_CUDA_OK(cudaMemsetAsync(bf.ca_cnt, 0, kCaSplitUnits * sizeof(int), stream));
-  const bool one_launch = small_enabled() && decode_small_applicable(dm, B, n_q) && m.dec_dev != nullptr && st->max_pages <= 32;
+  const bool one_launch = small_enabled(B) && decode_small_applicable(dm, B, n_q) && m.dec_dev != nullptr && st->max_pages <= 32;
   if (one_launch) {
     // K13: the whole step (all layers, both attentions, final LayerNorm and the logits) as one cooperative launch
     B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, kChainCounters * sizeof(unsigned int), stream));
