@@ -554,6 +554,78 @@ def case_filter_argmax():
 # bf16 tolerance (stated): activations are stored in bf16 (8 significant bits, 2^-9 relative rounding);
 # against the fp32 oracle the encoder states (unit scale after ln_post) must agree to 5e-2 max-abs and
 # 6e-3 mean-abs; against the oracle run with the same 16-bit storage policy to 3e-2 / 3e-3.
+def case_sampling_distribution():
+    """T > 0 (the reference's `categorical(logits / T)`, used by the temperature fallback): the on-device Gumbel-max
+    sampler is checked against the distribution it has to draw from -- 8192 sequences with the same filtered logits,
+    empirical token frequencies vs softmax(filtered / T) within 5 sigma, no forbidden token ever drawn, and the
+    log-probability bookkeeping (log_softmax of the UNTEMPERED filtered logits at the drawn token, as in
+    GreedyDecoder.update) against the oracle's."""
+    from oracle import decoding as OD
+    from oracle.tokens import TokenIds
+
+    L, lib = _lib()
+    out = {}
+    n_vocab = 51866
+    ids = TokenIds(n_vocab)
+    tb, eot, sb = ids.timestamp_begin, ids.eot, 3
+    ld = ((n_vocab + 127) // 128) * 128
+    pre = list(ids.sot_sequence("en"))
+    B = 8192
+    for (hist, T) in (([tb + 10, 400], 0.6), ([tb + 10, 400, tb + 60, tb + 60, 500], 1.0)):
+        rng = np.random.default_rng(int(T * 10))
+        row = rng.standard_normal(ld).astype(np.float32)
+        hot_text = rng.choice(np.arange(1000, 40000), size=6, replace=False)
+        row[hot_text] += np.array([9.0, 8.5, 8.0, 7.0, 6.0, 5.0], dtype=np.float32)
+        row[tb + 70: tb + 73] += np.array([8.0, 7.0, 6.0], dtype=np.float32)
+        row[eot] += 6.5
+        toks = np.array([pre + hist], dtype=np.int64)
+        filt = row[None, :n_vocab].copy()
+        OD.filter_logits(filt, toks, sb, ids, ids.suppress_set())
+        ft = torch.from_numpy(filt[0]).double()
+        p_ref = torch.softmax(ft / T, dim=-1)
+        lp_ref = torch.log_softmax(ft, dim=-1)
+
+        n = toks.shape[1]
+        tok_c = torch.zeros((B, 460), dtype=torch.int32)
+        tok_c[:, :n] = torch.from_numpy(toks[0]).int()
+        tok_c = tok_c.cuda()
+        ntok = torch.full((B,), n, dtype=torch.int32).cuda()
+        pos = torch.zeros(B, dtype=torch.int32).cuda()
+        slp = torch.zeros(B, dtype=torch.float32).cuda()
+        fin = torch.zeros(B, dtype=torch.int32).cuda()
+        bits = np.zeros((n_vocab + 31) // 32, dtype=np.uint32)
+        for t in ids.suppress_set():
+            bits[t >> 5] |= np.uint32(1 << (t & 31))
+        bits_c = torch.from_numpy(bits.view(np.int32)).cuda()
+        fp = L.FilterParams(n_vocab=n_vocab, logits_ld=ld, sample_begin=sb, eot=eot, blank=220,
+                            no_timestamps=ids.no_timestamps, timestamp_begin=tb, no_speech=ids.no_speech,
+                            max_initial_timestamp_index=50, apply_timestamp_rules=1, suppress_blank=1,
+                            tokens_ld=460, temperature=T, seed=1234)
+        lg = torch.from_numpy(row).cuda()[None].expand(B, ld).contiguous()
+        L.check(lib.b200w_filter_argmax(L.ptr(lg), L.ptr(bits_c), L.ptr(tok_c), L.ptr(ntok), L.ptr(pos), L.ptr(slp),
+                                        L.ptr(fin), B, C.byref(fp), L.stream()))
+        torch.cuda.synchronize()
+        drawn = tok_c[:, n].cpu().long()
+        assert bool(torch.isfinite(ft[drawn]).all()), "a token the rules forbid was drawn"
+        counts = torch.bincount(drawn, minlength=n_vocab).double()
+        support = torch.nonzero(p_ref > 1e-3)[:, 0]
+        worst = 0.0
+        for v in support.tolist():
+            pv = float(p_ref[v])
+            sigma = (B * pv * (1 - pv)) ** 0.5
+            z = abs(float(counts[v]) - B * pv) / sigma
+            worst = max(worst, z)
+            assert z <= 5.0, (T, v, float(counts[v]), B * pv, sigma)
+        rest = float(counts.sum() - counts[support].sum()) / B
+        assert abs(rest - float(1 - p_ref[support].sum())) <= 0.01
+        e_lp = (slp.cpu().double() - lp_ref[drawn]).abs().max().item()
+        assert e_lp <= 2e-4 * max(1.0, float(lp_ref[drawn].abs().max())), e_lp
+        assert torch.equal(fin.cpu().long(), (drawn == eot).long())
+        out[f"T{T}"] = {"support": len(support), "worst_sigma": worst, "distinct_drawn": int((counts > 0).sum()), "logprob_err": e_lp}
+        assert int((counts > 0).sum()) >= len(support)
+    return out
+
+
 def case_encoder_tiny():
     from oracle import audio as OA, model as OM
 
@@ -1086,6 +1158,7 @@ CASES = {
     "absorbed_cross_attention": case_absorbed_cross_attention,
     "logmel_pcm16": case_logmel_pcm16,
     "filter_argmax": case_filter_argmax,
+    "sampling_distribution": case_sampling_distribution,
     "encoder_tiny": case_encoder_tiny,
     "decoder_tiny": case_decoder_tiny,
     "decode_tiny": case_decode_tiny,
