@@ -263,14 +263,18 @@ def logmel_rooflines(peaks, device, batch: int = 1024, clocks_mhz: float = None)
     if os.path.exists(p):
         table = {int(k): float(v) for k, v in json.load(open(p)).items()}
     for n_mels in (80, 128):
-        t = _timed(lambda i=0: log_mel_spectrogram(x, n_mels=n_mels), 5)
+        res = torch.empty((batch, 3000, n_mels), dtype=torch.float32, device=device)  # (the result buffer is reused)
+        t = _timed(lambda i=0: log_mel_spectrogram(x, n_mels=n_mels, out=res), 5)
+        del res
         bytes_alg = batch * (4 * 480000 + 4 * 3000 * n_mels)
         frames_per_s = batch * 3000 / t
         sm_hz = (clocks_mhz or 1900.0) * 1e6
         issue_ceiling = 148 * 4 * sm_hz / table[n_mels]  # frames/s if every issue slot of every SM held a useful instruction
         out[f"logmel_{n_mels}"] = {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                   "frac": bytes_alg / t / 1e9 / peaks["hbm_gbs"], "traffic": None, "launch_ms": t * 1e3,
-                                   "frames_per_s": frames_per_s, "algorithmic_bytes_per_launch": bytes_alg,
+                                   "frac": bytes_alg / t / 1e9 / peaks["hbm_gbs"],
+                                   # dram read + write of the ncu --set full capture at 1024 windows (profiles/r02_ncu_full_summaries.json)
+                                   "traffic": (1_968_447_000 + 1_537_237_000) * batch / 1024.0 if n_mels == 128 else None,
+                                   "launch_ms": t * 1e3, "frames_per_s": frames_per_s, "algorithmic_bytes_per_launch": bytes_alg,
                                    "fp32_issue_ceiling_frames_per_s": issue_ceiling, "fp32_issue_frac": frames_per_s / issue_ceiling,
                                    "warp_instr_per_frame": table[n_mels], "issue_clock_mhz": sm_hz / 1e6}
     return out

@@ -182,7 +182,8 @@ def _to_device_audio(audio, device=None) -> torch.Tensor:
     return audio.to(torch.int16 if audio.dtype == torch.int16 else torch.float32).contiguous()
 
 
-def _run_logmel(audio: torch.Tensor, n_mels: int, padding: int, normalized: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+def _run_logmel(audio: torch.Tensor, n_mels: int, padding: int, normalized: bool,
+                out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     x = audio if audio.ndim == 2 else audio[None]
     _lib.require_cuda(x, "audio")
@@ -194,7 +195,10 @@ def _run_logmel(audio: torch.Tensor, n_mels: int, padding: int, normalized: bool
         x = torch.zeros((n_audio, 1), dtype=x.dtype, device=x.device)
     n_frames = n_total // HOP_LENGTH
     tb = _get_tables(x.device, n_mels)
-    out = torch.empty((n_audio, n_frames, n_mels), dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty((n_audio, n_frames, n_mels), dtype=torch.float32, device=x.device)
+    elif out.shape != (n_audio, n_frames, n_mels) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+        raise ValueError(f"out must be a contiguous f32 tensor of shape {(n_audio, n_frames, n_mels)} on {x.device}")
     gmax = torch.empty((n_audio,), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         if normalized:
@@ -218,22 +222,23 @@ def log_mel_unclamped(audio: torch.Tensor, n_mels: int = 80, padding: int = 0) -
 
 
 def log_mel_spectrogram(audio: Union[str, np.ndarray, torch.Tensor], n_mels: int = 80, padding: int = 0,
-                        device=None) -> torch.Tensor:
+                        device=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Log-mel spectrogram, (frames, n_mels) f32 on the GPU, time-major like the reference.
 
     `audio`: path (decoded with ffmpeg), NumPy array or torch tensor of 16 kHz mono samples in [-1, 1] (int16
     arrays are taken as s16le PCM and scaled by 1/32768 on the device);
     `padding` zero samples are appended first.  A 2-D input (n_audio, n) gives (n_audio, frames, n_mels)
-    with one clamp maximum per row (the batched contract of BASELINE config 2).
+    with one clamp maximum per row (the batched contract of BASELINE config 2).  `out` (not in the reference): a
+    preallocated (n_audio, frames, n_mels) f32 result buffer to write into instead of allocating one per call.
     """
     x = _to_device_audio(audio, device)
     batched = x.ndim == 2
     if os.environ.get("B200W_LOGMEL_TWO_PASS") == "1":  # A/B: the r01 form, clamp as a second pass over the result
-        out, gmax = log_mel_unclamped(x, n_mels, padding)
+        out, gmax = _run_logmel(x, n_mels, padding, normalized=False, out=out)
         lib = _lib.load()
         with torch.cuda.device(out.device):
             _lib.check(lib.b200w_logmel_finalize(_lib.ptr(out), _lib.ptr(gmax), out.shape[0], out.shape[1] * out.shape[2],
                                                  _lib.stream()))
     else:
-        out, _ = _run_logmel(x, n_mels, padding, normalized=True)
+        out, _ = _run_logmel(x, n_mels, padding, normalized=True, out=out)
     return out if batched else out[0]

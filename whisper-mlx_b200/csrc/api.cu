@@ -1017,6 +1017,7 @@ int b200w_dtw(const float* matrix, long long ld, int N, int M, float* cost, sign
 }
 
 int b200w_debug_chain_mc_grid() { return chain_mc_grid(); }
+void b200w_debug_chain_timeline(long long* dev, int launch_index) { set_chain_timeline(dev, launch_index); }
 
 int b200w_debug_mma_bench(int m, int n, int a_mn, int ts, int reps, long long* cycles, void* stream) {
   return launch_absorb_mma_bench(m, n, a_mn, ts, reps, cycles, (cudaStream_t)stream);

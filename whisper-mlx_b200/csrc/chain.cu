@@ -62,8 +62,12 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
-// All CTAs of the (cooperative, co-resident) grid meet here; `target` = CTAs x barriers passed so far.
-__device__ __forceinline__ void chain_grid_barrier(unsigned int* counter, unsigned int target) {
+// All CTAs of the (cooperative, co-resident) grid meet here; `target` = CTAs x barriers passed so far.  `between` runs in
+// thread 0 after the CTA's arrival and before the poll: work that does not depend on the barrier (the weight prefetch of the
+// next GEMM phase) stays off every other CTA's critical path -- issued before the arrival it delayed the whole grid by the
+// ~1.7 us it takes one thread to put 8 TMA loads in flight (tools/probe_chain_timeline.py).
+template <typename F>
+__device__ __forceinline__ void chain_grid_barrier(unsigned int* counter, unsigned int target, F&& between) {
   fence_proxy_async_global();  // this thread's generic-proxy global writes are ordered before later TMA reads
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -71,6 +75,7 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned int* counter, unsign
     // arrival; acquire on the poll orders everything after it.  Explicit __threadfence() on both sides measured
     // 1.84 us per barrier (tools/probe_chain.py); the two fences are implied by .release / .acquire.
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");  // no return value to wait for
+    between();
     unsigned int spins = 0;
     while (ld_acquire_gpu(counter) < target) {
       if (++spins > (1u << 26)) __trap();  // a lost CTA must not hang the GPU
@@ -161,8 +166,13 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     }
   };
 
+  const int tl_cta = (p.timeline == nullptr) ? -1 : (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x / 2 ? 1 : -1));
+  auto stamp = [&](int ph, int k) {
+    if (tl_cta >= 0) p.timeline[(tl_cta * kChainMaxPhases + ph) * 8 + k] = clock64();
+  };
   for (int ph = 0; ph < p.n_phases; ++ph) {
     const ChainPhase& P = p.ph[ph];
+    if (tid == 0) stamp(ph, 0);  // phase start
     if (P.kind == kChainGemm) {
       // work items of this CTA's group: (column tile [group], row tile, K slice), K slice fastest
       const int num_tiles = (P.tiles_n / kGroup) * p.tiles_m * P.split_k;
@@ -199,6 +209,7 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
               }
             }
           }
+          stamp(ph, 1);  // this phase's loads are issued
           pre_cnt = 0;
           if (ph + 1 < p.n_phases && p.ph[ph + 1].kind == kChainGemm) prefetch_w(p.ph[ph + 1]);
         }
@@ -215,6 +226,7 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
             for (int kb = kb_begin; kb < kb_end; ++kb) {
               mbar_wait(&full_bar[stage], ring_phase);
               tcgen05_fence_after();
+              if (kb == kb_begin && tile == worker) stamp(ph, 2);  // first operands landed
               const uint32_t sa = smem_u32(smem + stage * kChStageBytes);
               const uint64_t a_desc = make_sw128_desc(sa);
               const uint64_t b_desc = make_sw128_desc(sa + kChABytes);
@@ -229,6 +241,7 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
               }
             }
             umma_commit(&tmem_full_bar[acc]);
+            if (tile + n_workers >= num_tiles) stamp(ph, 3);  // last MMA issued
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
           }
@@ -246,6 +259,7 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
           const int rows_here = min(32, p.rows - t0);
           mbar_wait(&tmem_full_bar[acc], acc_phase);
           tcgen05_fence_after();
+          if (warp == 4 && lane == 0 && tile + n_workers >= num_tiles) stamp(ph, 4);  // last accumulator complete
           const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kChBN;
           const int col = nt * kChBN + hh * 32;
           uint32_t r[32];
@@ -329,11 +343,17 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         }
       }
     }
-    if (P.kind == kChainLn) {  // (a GEMM phase's producer has already done this at the end of its loop)
-      if (tid == 0 && ph + 1 < p.n_phases && p.ph[ph + 1].kind == kChainGemm) prefetch_w(p.ph[ph + 1]);
-      __syncwarp();
+    if (warp == 4 && lane == 0) stamp(ph, 5);  // epilogue warp 4 done with the phase
+    if (ph + 1 < p.n_phases) {
+      if (tid == 0) stamp(ph, 6);  // arrives at the grid barrier (before the CTA-wide sync)
+      // after a LayerNorm phase the producer thread puts the next GEMM's weight tiles in flight while it waits (a GEMM
+      // phase's producer has already done this at the end of its loop, under the phase's own MMAs)
+      const bool pre = P.kind == kChainLn && p.ph[ph + 1].kind == kChainGemm;
+      chain_grid_barrier(p.counter, (unsigned int)(ph + 1) * gridDim.x, [&]() {
+        if (pre) prefetch_w(p.ph[ph + 1]);
+      });
+      if (tid == 0) stamp(ph, 7);  // released
     }
-    if (ph + 1 < p.n_phases) chain_grid_barrier(p.counter, (unsigned int)(ph + 1) * gridDim.x);
   }
 
   tcgen05_fence_before();
@@ -343,6 +363,13 @@ decode_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kChTmemCols);
   }
+}
+
+static long long* g_chain_timeline = nullptr;
+static int g_chain_timeline_countdown = -1;
+void set_chain_timeline(long long* dev, int launch_index) {
+  g_chain_timeline = dev;
+  g_chain_timeline_countdown = dev ? launch_index : -1;
 }
 
 static int g_chain_mc_grid = 0;  // CTAs of the multicast form that can be co-resident (0: unavailable)
@@ -462,10 +489,13 @@ int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t strea
   cfg.attrs = attr;
   cfg.numAttrs = mc ? 2 : 1;
   ProfScope prof_("dec_chain", stream);
+  ChainParams pl = p;
+  pl.timeline = nullptr;
+  if (g_chain_timeline_countdown >= 0 && g_chain_timeline_countdown-- == 0) pl.timeline = g_chain_timeline;
   if (mc)
-    B200W_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_chain_kernel<true>, maps, p));
+    B200W_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_chain_kernel<true>, maps, pl));
   else
-    B200W_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_chain_kernel<false>, maps, p));
+    B200W_CUDA_OK(cudaLaunchKernelEx(&cfg, decode_chain_kernel<false>, maps, pl));
   count_launch();
   return kOk;
 }

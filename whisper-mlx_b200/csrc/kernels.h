@@ -89,6 +89,7 @@ struct ChainParams {
   int n_phases, n_gemm, rows;
   int tiles_m;            // 128-row tiles (1 or 2), set by chain_add_gemm
   unsigned int* counter;  // zero on entry; one per launch
+  long long* timeline;    // development aid (tools/probe_chain_timeline.py): clock64 stamps, 8 per phase for 2 CTAs, or null
   ChainPhase ph[kChainMaxPhases];
 };
 struct ChainMaps {
@@ -102,6 +103,7 @@ int chain_add_gemm(ChainMaps* maps, ChainParams* p, const void* A, long long lda
 int chain_add_ln(ChainParams* p, float* x, const float* part, int n_split, long long split_stride, const float* bias,
                  const float* gamma, const float* beta, int d, __nv_bfloat16* h);
 int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t stream);
+void set_chain_timeline(long long* dev, int launch_index);  // stamps go to the launch_index-th chain launch from now
 
 // ---------------------------------------------------------------------------------------- K13 small-batch decode step
 // One cooperative launch for a whole single-token decoder step of <= kSmallMaxBatch sequences (small.cu).
