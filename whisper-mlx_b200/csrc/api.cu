@@ -780,7 +780,7 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
     //   [LN -> QKV]  SA  [out -> LN -> q]  CA  [out -> LN -> MLP1 -> MLP2 -> LN -> next layer's QKV]
     const long long s3 = (long long)rows_pad * 3 * d, s1 = (long long)rows_pad * d;
     const bool mcp = use_mc_plan(rows, d);
-    const int grp = mcp ? 4 : 1, wk = mcp ? chain_mc_grid() / 4 : 0, tm = rows_pad / 128;
+    const int grp = mcp ? chain_mc_cluster() : 1, wk = mcp ? chain_mc_grid() / chain_mc_cluster() : 0, tm = rows_pad / 128;
     const int sp_qkv = plan_split_k(3 * d, d, 64, grp, wk, tm), sp_d = plan_split_k(d, d, 64, grp, wk, tm),
               sp_mlp2 = plan_split_k(d, 4 * d, 64, grp, wk, tm);
     B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, kChainCounters * sizeof(unsigned int), stream));
@@ -846,7 +846,7 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
     const int bn = 64;
     const long long s3 = 128ll * 3 * d, s1 = 128ll * d;
     const bool mcp = use_mc_plan(rows, d);
-    const int grp = mcp ? 4 : 1, wk = mcp ? chain_mc_grid() / 4 : 0;
+    const int grp = mcp ? chain_mc_cluster() : 1, wk = mcp ? chain_mc_grid() / chain_mc_cluster() : 0;
     const int sp_qkv = plan_split_k(3 * d, d, bn, grp, wk), sp_d = plan_split_k(d, d, bn, grp, wk),
               sp_mlp2 = plan_split_k(d, 4 * d, bn, grp, wk);
     int pend = 0;  // split count of the residual GEMM whose partials (+ bias) the next LayerNorm folds into x

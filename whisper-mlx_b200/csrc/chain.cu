@@ -89,7 +89,10 @@ __device__ __forceinline__ void chain_grid_barrier(unsigned int* counter, unsign
 // every CTA loads a quarter of the 128 x 64 A tile and multicasts it to the cluster, so a CTA ingests 4 + 8 KB per K
 // block instead of 16 + 8 KB (the <= 128-row GEMMs are bound by the per-SM operand ingest; the same activations used
 // to be fetched by every CTA).  A stage is released to its four producers by the four MMA issuers (multicast commit).
-constexpr int kChCluster = 4;
+#ifndef B200W_CHAIN_CLUSTER
+#define B200W_CHAIN_CLUSTER 4
+#endif
+constexpr int kChCluster = B200W_CHAIN_CLUSTER;
 
 template <bool MC>
 __global__ void __launch_bounds__(kChThreads, 1)
@@ -409,6 +412,8 @@ int init_chain() {
 }
 
 // ---------------------------------------------------------------------------------------------- host
+int chain_mc_cluster() { return kChCluster; }
+
 int chain_mc_grid() {
   if (init_chain() != kOk) return -1;
   return g_chain_mc_grid;

@@ -98,6 +98,7 @@ struct ChainMaps {
 };
 int init_chain();
 int chain_mc_grid();  // CTAs of the cluster-multicast form that fit at once (0: form unavailable)
+int chain_mc_cluster();  // CTAs per cluster of that form
 int chain_add_gemm(ChainMaps* maps, ChainParams* p, const void* A, long long lda, const void* W, int N, int K, int split_k,
                    void* out, long long ldc, long long split_stride, const float* bias, bool gelu);
 int chain_add_ln(ChainParams* p, float* x, const float* part, int n_split, long long split_stride, const float* bias,
