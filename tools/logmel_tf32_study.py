@@ -17,8 +17,8 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import audio as OA  # noqa: E402  (test infrastructure; this is a study tool, not the product)
 from tools import synth  # noqa: E402
+from whisper_mlx_b200.audio import mel_filters  # noqa: E402
 
 
 def tf32(x):
@@ -81,7 +81,7 @@ def power_spectrum(fr, mode):
 
 
 def logmel_from_power(p, n_mels):
-    mel = p.astype(np.float32) @ OA.mel_filters(n_mels).T
+    mel = p.astype(np.float32) @ np.asarray(mel_filters(n_mels), dtype=np.float32).T
     lm = np.log10(np.maximum(mel, 1e-10))
     lm = np.maximum(lm, lm.max() - 8.0)
     return (lm + 4.0) / 4.0
