@@ -19,7 +19,7 @@ for i in range(2):
 dm = model.dims
 for small in ("1", "0"):
     os.environ["B200W_SMALL"] = small
-    for B in (1, 5):
+    for B in (1, 2, 3, 5):
         xa = torch.randn(B, dm.n_audio_ctx, dm.n_audio_state, device="cuda").bfloat16()
         task = DecodingTask(model, DecodingOptions(language="en"))
         sess = DecodeSession(model, xa, 1, max_tokens=3 + 224)

@@ -843,6 +843,189 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
   }
 }
 
+// K8r: the decode-step form for full batches (n_q == 1, one CTA per (sequence, head), no key split, no probability
+// output).  Same arithmetic as K8 above, but the K / V rows do not pass through registers on their way in: every
+// thread owns kRing 16-byte slots of shared memory and keeps them filled with cp.async (LDGSTS), consuming slot i while
+// slots i + 1 .. i + kRing - 1 are in flight.  K8 issues 8 loads, waits for all of them, computes, and only then issues
+// the next 8 -- its bytes in flight swing between 32 KB and 0 per CTA and it stops at 0.95 of the COPY bandwidth
+// (6.3 TB/s), while a read-only stream with >= 64 KB per SM continuously in flight reaches 7.3 TB/s on this part
+// (tools/probes/probe_read.cu).  Here the stream is continuous from the first instruction of the CTA (the loads are
+// in flight while the query is reduced from its split-K slabs) across the K -> V transition (V rows are requested
+// before the softmax barriers) to the end.  A thread reads back only what it copied itself: cp.async.wait_group is
+// all the synchronisation the ring needs.
+#ifndef B200W_CROSS_RING
+#define B200W_CROSS_RING 10
+#endif
+constexpr int kRing = B200W_CROSS_RING;
+constexpr int kCrossRingSmem = kRing * kCrossThreads * 16;
+#ifndef B200W_CROSS_RING_CTAS
+#define B200W_CROSS_RING_CTAS 4
+#endif
+
+__device__ __forceinline__ void cross_cp16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cross_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cross_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kCrossThreads, B200W_CROSS_RING_CTAS)
+decoder_cross_attention_ring_kernel(int n_head, const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride, int T,
+                                    const int* __restrict__ slot, __nv_bfloat16* __restrict__ out,
+                                    const __nv_bfloat16* __restrict__ q, const float* __restrict__ part, int n_split,
+                                    long long split_stride, const float* __restrict__ bias, const int* __restrict__ finished) {
+  extern __shared__ __align__(16) unsigned char cross_ring_raw[];
+  uint4* ring = reinterpret_cast<uint4*>(cross_ring_raw);  // [kRing][kCrossThreads]
+  __shared__ float s_p[kMaxCrossKeys];
+  __shared__ float s_red[kCrossWarps];
+  __shared__ float s_part[kCrossWarps][kHd];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & 7, kg = lane >> 3;
+  const int d = n_head * kHd;
+  const long long ld = 2ll * d;
+  const int h = blockIdx.y, b = blockIdx.z;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (finished != nullptr && finished[b]) return;
+  const __nv_bfloat16* kbase = cross_kv + (long long)slot[b] * seq_stride + h * kHd + sub * 8;
+  constexpr int kStep = kCrossWarps * 4;     // keys per CTA per iteration
+  const int n_it = (T + kStep - 1) / kStep;  // iterations of the K stream; the V stream follows with the same count
+  const int total = 2 * n_it;
+  const int jt = warp * 4 + kg;              // this thread's key within an iteration
+  auto request = [&](int s, int fill) {      // stream position s -> ring slot `fill`
+    if (s < total) {
+      const bool is_v = s >= n_it;
+      const int j = min(jt + (is_v ? s - n_it : s) * kStep, T - 1);
+      cross_cp16(ring + fill * kCrossThreads + tid, kbase + (is_v ? d : 0) + j * ld);
+    }
+    cross_commit();  // (an empty group keeps the count uniform)
+  };
+#pragma unroll
+  for (int s = 0; s < kRing - 1; ++s) request(s, s);
+
+  float qv[8];
+  if (n_split > 0) {
+    // q arrives as split-K fp32 partial slabs of the query projection (+ bias): reduce, round to bf16
+    const long long col = (long long)b * d + h * kHd + sub * 8;
+    const float c = 0.125f * kLog2e;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = bias[h * kHd + sub * 8 + i];
+    for (int sidx = 0; sidx < n_split; ++sidx) {
+      const float4 a = *reinterpret_cast<const float4*>(part + sidx * split_stride + col);
+      const float4 e = *reinterpret_cast<const float4*>(part + sidx * split_stride + col + 4);
+      qv[0] += a.x; qv[1] += a.y; qv[2] += a.z; qv[3] += a.w;
+      qv[4] += e.x; qv[5] += e.y; qv[6] += e.z; qv[7] += e.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = __bfloat162float(__float2bfloat16(qv[i])) * c;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(q + (long long)b * d + h * kHd + sub * 8);
+    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+    const float c = 0.125f * kLog2e;
+    qv[0] = a0.x * c; qv[1] = a0.y * c; qv[2] = a1.x * c; qv[3] = a1.y * c;
+    qv[4] = a2.x * c; qv[5] = a2.y * c; qv[6] = a3.x * c; qv[7] = a3.y * c;
+  }
+
+  int cons = 0, fill = kRing - 1;  // slot to consume; slot to refill (the one consumed an iteration ago)
+  auto next = [&](int s) -> uint4 {  // the row at stream position s; requests position s + kRing - 1
+    cross_wait<kRing - 2>();
+    const uint4 u = ring[cons * kCrossThreads + tid];
+    request(s + kRing - 1, fill);
+    fill = cons;
+    cons = (cons + 1 == kRing) ? 0 : cons + 1;
+    return u;
+  };
+
+  // ---- scores ----
+  float mx = -INFINITY;
+  for (int i = 0; i < n_it; ++i) {
+    const uint4 u = next(i);
+    const int j = jt + i * kStep;
+    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+    float s = a0.x * qv[0];
+    s = fmaf(a0.y, qv[1], s);
+    s = fmaf(a1.x, qv[2], s);
+    s = fmaf(a1.y, qv[3], s);
+    s = fmaf(a2.x, qv[4], s);
+    s = fmaf(a2.y, qv[5], s);
+    s = fmaf(a3.x, qv[6], s);
+    s = fmaf(a3.y, qv[7], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (j < T) {
+      if (sub == 0) s_p[j] = s;
+      mx = fmaxf(mx, s);
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int i = 1; i < kCrossWarps; ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
+  float sum = 0.0f;
+  for (int j = tid; j < T; j += kCrossThreads) {
+    const float p = fast_exp2(s_p[j] - mx);
+    sum += p;
+    s_p[j] = __bfloat162float(__float2bfloat16(p));  // bf16 probabilities, as in the tensor-core path
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kCrossWarps; ++i) sum += s_red[i];
+
+  // ---- output ----
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < n_it; ++i) {
+    const uint4 u = next(n_it + i);
+    const int j = jt + i * kStep;
+    const float p = (j < T) ? s_p[j] : 0.0f;
+    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+    acc[0] = fmaf(p, a0.x, acc[0]);
+    acc[1] = fmaf(p, a0.y, acc[1]);
+    acc[2] = fmaf(p, a1.x, acc[2]);
+    acc[3] = fmaf(p, a1.y, acc[3]);
+    acc[4] = fmaf(p, a2.x, acc[4]);
+    acc[5] = fmaf(p, a2.y, acc[5]);
+    acc[6] = fmaf(p, a3.x, acc[6]);
+    acc[7] = fmaf(p, a3.y, acc[7]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (kg == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_part[warp][sub * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < kHd) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kCrossWarps; ++w) v += s_part[w][tid];
+    out[(long long)b * d + h * kHd + tid] = __float2bfloat16(v / sum);
+  }
+}
+
+// B200W_CROSS_STREAM=0 keeps the register-staged K8 for every shape (A/B)
+static bool cross_ring_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200W_CROSS_STREAM");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    if (v) v = cudaFuncSetAttribute(decoder_cross_attention_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrossRingSmem) == cudaSuccess ? 1 : 0;
+  }
+  return v != 0;
+}
+
 int cross_attention_kv_splits(int n_seq, int n_q, int n_head) {
   const long long units = (long long)n_seq * n_q * n_head;
   const int s = (int)(device_sm_count() / (units > 0 ? units : 1));
@@ -859,6 +1042,12 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
   const int kv_splits = (kv_part != nullptr && kv_cnt != nullptr && probs_out == nullptr) ? cross_attention_kv_splits(n_seq, n_q, n_head) : 1;
   ProfScope prof_("decoder_cross_attention", stream);
+  if (kv_splits == 1 && probs_out == nullptr && n_q == 1 && cross_ring_enabled()) {
+    B200W_CUDA_OK(launch_k(decoder_cross_attention_ring_kernel, dim3(1, n_head, n_seq), dim3(kCrossThreads), (size_t)kCrossRingSmem,
+                           stream, n_head, cross_kv, seq_stride, T, slot, out, q, part, n_split, split_stride, bias, finished));
+    count_launch();
+    return kOk;
+  }
   if (kv_splits > 1) {
     dim3 grid(n_q, n_head * kv_splits, n_seq);
     B200W_CUDA_OK(launch_k(decoder_cross_attention_kernel<false, true>, grid, dim3(kCrossThreads), 0, stream, q, n_q, n_head,
