@@ -200,11 +200,23 @@ def kernel_rooflines(model, peaks, n_windows: int, with_logmel: bool = True):
                                                                      L.ptr(slot), L.ptr(o), L.stream())), 4 * Lr)
     bytes_alg = n_windows * T * 2 * d * 2  # K and V rows of every window, bf16, read once
     # DRAM traffic per launch from the ncu --set full capture of this kernel at 120 windows
-    # (profiles/r01_ncu_full_summaries_v2.json: 921.93 MB read + 4.27 MB written), scaled to this launch's windows
-    traffic = (921_940_480 + 4_274_944) * n_windows / 120.0 if d == 1280 else None
+    # (profiles/r02_ncu_cross_ring.json), scaled to this launch's windows
+    traffic = CROSS_DRAM_BYTES_AT_120 * n_windows / 120.0 if d == 1280 else None
+    # The kernel only READS: besides the copy bandwidth of MEASURED_PEAKS.json (half writes) it is held against a
+    # read-only stream of the same number of bytes, timed here the same way (b200w_debug_read_stream).
+    import ctypes as C
+
+    rs = lib.b200w_debug_read_stream
+    rs.restype, rs.argtypes = C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    sink = torch.zeros(2, dtype=torch.int64, device=model.device)
+    t_rd = _timed(lambda i=0: L.check(rs(L.ptr(ckv[i % Lr]), bytes_alg, L.ptr(sink), L.stream())), 4 * Lr)
+    read_gbs = bytes_alg / t_rd / 1e9
     out["decoder_cross_attention"] = {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                       "frac": bytes_alg / t / 1e9 / peaks["hbm_gbs"], "traffic": traffic, "launch_ms": t * 1e3,
-                                      "algorithmic_bytes_per_launch": bytes_alg}
+                                      "algorithmic_bytes_per_launch": bytes_alg, "read_only_stream_gbs": read_gbs,
+                                      "frac_of_read_only_stream": t_rd / t,
+                                      "note": "peak = copy bandwidth (MEASURED_PEAKS.json); read_only_stream_gbs = the same bytes "
+                                              "read linearly by a load-only kernel at the same launch size, timed here"}
     del ckv
     # K5 / K5b encoder GEMMs, all four shapes of a block: M = windows * 1500 rows, L2 flushed by the operand sizes
     M = min(n_windows, 40) * T
@@ -245,6 +257,9 @@ def kernel_rooflines(model, peaks, n_windows: int, with_logmel: bool = True):
         out.update(logmel_rooflines(peaks, model.device))
     return out
 
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one decoder_cross_attention_ring_kernel launch at 120 windows (ncu --set full)
+CROSS_DRAM_BYTES_AT_120 = 921_940_480 + 4_274_944
 
 # FP32-issue ceiling of the log-mel kernel: warp-instructions per frame from the ncu source view of the shipped kernel
 # (profiles/) against 4 warp-instructions per clock per SM on 148 SMs

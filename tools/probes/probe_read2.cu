@@ -73,6 +73,32 @@ __global__ void rows_kernel(const uint4* __restrict__ kv, size_t n16, unsigned l
   if (acc.x == 0x1234567) sink[0] = acc.x;
 }
 
+// one CTA per (sequence, group of G heads): a warp-instruction reads 32 / (8 * G) rows x (G x 128) contiguous bytes
+template <int U, int G>
+__global__ void group_kernel(const unsigned char* __restrict__ kv, unsigned long long* sink) {
+  constexpr int HG = H / G;
+  const int hg = blockIdx.x % HG, b = blockIdx.x / HG;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kLanesPerRow = 8 * G, kRowsPerWarp = 32 / kLanesPerRow, kRowsPerIt = 8 * kRowsPerWarp;
+  const int col = lane % kLanesPerRow, kg = lane / kLanesPerRow;
+  const unsigned char* base = kv + (long long)b * T * LD + hg * (G * 128) + col * 16;
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  for (int pass = 0; pass < 2; ++pass) {
+    const unsigned char* p = base + pass * (D * 2);
+    for (int j0 = warp * kRowsPerWarp; j0 < T; j0 += U * kRowsPerIt) {
+      uint4 u[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const int j = j0 + kg + i * kRowsPerIt;
+        u[i] = (j < T) ? __ldg(reinterpret_cast<const uint4*>(p + (long long)j * LD)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) acc.x ^= u[i].x ^ u[i].y ^ u[i].z ^ u[i].w;
+    }
+  }
+  if (acc.x == 0x1234567) sink[0] = acc.x;
+}
+
 template <typename F>
 static void timeit(const char* name, double bytes, F launch) {
   cudaEvent_t e0, e1;
@@ -108,6 +134,12 @@ int main() {
   timeit("persistent 4 CTAs/SM x 256 thr, 8 loads, units round-robin", (double)layer, [&] { persistent_kernel<8><<<sms * 4, 256>>>(buf(), sink); });
   timeit("persistent 8 CTAs/SM x 256 thr, 4 loads", (double)layer, [&] { persistent_kernel<4><<<sms * 8, 256>>>(buf(), sink); });
   timeit("persistent 8 CTAs/SM x 256 thr, 8 loads", (double)layer, [&] { persistent_kernel<8><<<sms * 8, 256>>>(buf(), sink); });
+  timeit("CTA per (seq, 2 heads) (1200 x 256 thr), 4 loads", (double)layer, [&] { group_kernel<4, 2><<<B * H / 2, 256>>>(buf(), sink); });
+  timeit("CTA per (seq, 2 heads) (1200 x 256 thr), 8 loads", (double)layer, [&] { group_kernel<8, 2><<<B * H / 2, 256>>>(buf(), sink); });
+  timeit("CTA per (seq, 4 heads) (600 x 256 thr), 4 loads", (double)layer, [&] { group_kernel<4, 4><<<B * H / 4, 256>>>(buf(), sink); });
+  timeit("CTA per (seq, 4 heads) (600 x 256 thr), 8 loads", (double)layer, [&] { group_kernel<8, 4><<<B * H / 4, 256>>>(buf(), sink); });
+  timeit("CTA per (seq, 4 heads) (600 x 256 thr), 16 loads", (double)layer, [&] { group_kernel<16, 4><<<B * H / 4, 256>>>(buf(), sink); });
+  timeit("CTA per (seq, 4 heads) (600 x 512 thr), 8 loads", (double)layer, [&] { group_kernel<8, 4><<<B * H / 4, 512>>>(buf(), sink); });
   timeit("contiguous rows, 4 CTAs/SM x 256 thr, 8 loads (same bytes)", (double)layer, [&] { rows_kernel<8><<<sms * 4, 256>>>((const uint4*)buf(), layer / 16, sink); });
   timeit("contiguous rows, 2400 CTAs x 256 thr, 8 loads", (double)layer, [&] { rows_kernel<8><<<B * H, 256>>>((const uint4*)buf(), layer / 16, sink); });
   return 0;

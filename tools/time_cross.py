@@ -3,7 +3,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from whisper_mlx_b200 import _lib as L
 lib = L.load()
-B, T, H, d = 120, 1500, 20, 1280
+B, T, H, d = (int(sys.argv[1]) if len(sys.argv) > 1 else 120), 1500, 20, 1280
 ckv = torch.randn(3, B, T, 2 * d, device="cuda").bfloat16()
 q = torch.randn(B, 1, d, device="cuda").bfloat16()
 o = torch.empty_like(q)
@@ -16,4 +16,4 @@ for i in range(15):
     e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
-print(os.environ.get("B200W_LIB", "default"), "CA us", [round(t, 1) for t in sorted(ts)[:5]])
+print(os.environ.get("B200W_LIB", "default"), "B", B, "CA us", [round(t, 1) for t in sorted(ts)[:5]])

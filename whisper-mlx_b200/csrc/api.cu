@@ -360,6 +360,26 @@ struct b200w_model {
   Model m;
 };
 
+namespace b200w {
+__global__ void __launch_bounds__(256) read_stream_kernel(const uint4* __restrict__ src, size_t n16, unsigned long long* sink) {
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 7 * stride < n16; i += 8 * stride) {
+    uint4 u[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] = __ldg(src + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc.x ^= u[k].x ^ u[k].y ^ u[k].z ^ u[k].w;
+  }
+  for (; i < n16; i += stride) {
+    const uint4 u = __ldg(src + i);
+    acc.x ^= u.x ^ u.y ^ u.z ^ u.w;
+  }
+  if (acc.x == 0x12345678u) sink[0] = acc.x;  // (practically never true: keeps the loads alive)
+}
+}  // namespace b200w
+
 extern "C" {
 
 const char* b200w_version(void) { return "b200-whisper 0.1 (abi 1, sm_100a)"; }
@@ -1037,6 +1057,16 @@ int b200w_debug_absorb_probe(const void* x, const void* q, const void* p, unsign
 void b200w_debug_small_timeline(void* dev_buf) { set_decode_small_timeline(static_cast<unsigned long long*>(dev_buf)); }
 
 // development probe (tools/probe_chain.py; not part of the public header): a chain of n_phases empty phases, i.e.
+// Read-only streaming of `bytes` (multiple of 16) with 4 CTAs of 256 threads per SM and 8 x 16 B in flight per thread:
+// the bandwidth ceiling of a kernel that only READS HBM (bench.py holds the cross-attention against it beside the
+// copy bandwidth of MEASURED_PEAKS.json, which is half writes).  tools/probes/probe_read.cu is the standalone form.
+int b200w_debug_read_stream(const void* buf, size_t bytes, void* sink, void* stream) {
+  B200W_CHECK_ARG(buf && sink && bytes % 16 == 0, "debug_read_stream: bad arguments");
+  B200W_CUDA_OK(launch_k(b200w::read_stream_kernel, dim3(b200w::device_sm_count() * 4), dim3(256), 0, (cudaStream_t)stream,
+                         static_cast<const uint4*>(buf), bytes / 16, static_cast<unsigned long long*>(sink)));
+  return kOk;
+}
+
 // n_phases - 1 grid barriers and nothing else
 int b200w_debug_chain_barriers(int n_phases, unsigned int* counter, float* x, void* h, const float* gamma, void* stream) {
   ChainMaps maps{};

@@ -854,9 +854,10 @@ decoder_cross_attention_kernel(const __nv_bfloat16* __restrict__ q, int n_q, int
 // before the softmax barriers) to the end.  A thread reads back only what it copied itself: cp.async.wait_group is
 // all the synchronisation the ring needs.
 #ifndef B200W_CROSS_RING
-#define B200W_CROSS_RING 10
+#define B200W_CROSS_RING 8
 #endif
-constexpr int kRing = B200W_CROSS_RING;
+constexpr int kRing = B200W_CROSS_RING;  // a power of two: slot = position & (kRing - 1)
+static_assert((kRing & (kRing - 1)) == 0 && kRing >= 4, "ring size");
 constexpr int kCrossRingSmem = kRing * kCrossThreads * 16;
 #ifndef B200W_CROSS_RING_CTAS
 #define B200W_CROSS_RING_CTAS 4
@@ -868,14 +869,26 @@ __device__ __forceinline__ void cross_cp16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cross_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cross_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// eight bf16 -> f32 with one integer instruction each (shift / mask)
+__device__ __forceinline__ void cross_unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
 
+// The kernel issues 58 -> 40 warp-instructions per 512 bytes in this form (ncu r02: the first ring version ran at
+// 78 % issue-active -- co-limited by instruction issue, not only by HBM): the source pointer advances by a constant,
+// the K -> V switch and the clamp of the last (partial) iteration live in peeled iterations instead of selects in the
+// loop, ring slots are position & (kRing - 1), scores of the padding keys (duplicates of key T - 1, so the maximum is
+// unaffected) are stored unconditionally and their probabilities zeroed once, bf16 pairs unpack with a shift and a mask.
 __global__ void __launch_bounds__(kCrossThreads, B200W_CROSS_RING_CTAS)
 decoder_cross_attention_ring_kernel(int n_head, const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride, int T,
                                     const int* __restrict__ slot, __nv_bfloat16* __restrict__ out,
                                     const __nv_bfloat16* __restrict__ q, const float* __restrict__ part, int n_split,
                                     long long split_stride, const float* __restrict__ bias, const int* __restrict__ finished) {
   extern __shared__ __align__(16) unsigned char cross_ring_raw[];
-  uint4* ring = reinterpret_cast<uint4*>(cross_ring_raw);  // [kRing][kCrossThreads]
+  uint4* ring = reinterpret_cast<uint4*>(cross_ring_raw) + threadIdx.x;  // [kRing][kCrossThreads], this thread's column
   __shared__ float s_p[kMaxCrossKeys];
   __shared__ float s_red[kCrossWarps];
   __shared__ float s_part[kCrossWarps][kHd];
@@ -888,21 +901,29 @@ decoder_cross_attention_ring_kernel(int n_head, const __nv_bfloat16* __restrict_
   pdl_wait();
   pdl_launch_dependents();
   if (finished != nullptr && finished[b]) return;
-  const __nv_bfloat16* kbase = cross_kv + (long long)slot[b] * seq_stride + h * kHd + sub * 8;
   constexpr int kStep = kCrossWarps * 4;     // keys per CTA per iteration
-  const int n_it = (T + kStep - 1) / kStep;  // iterations of the K stream; the V stream follows with the same count
-  const int total = 2 * n_it;
+  const int n_it = (T + kStep - 1) / kStep;  // iterations of the K stream (>= kRing: checked by the launcher); V follows
   const int jt = warp * 4 + kg;              // this thread's key within an iteration
-  auto request = [&](int s, int fill) {      // stream position s -> ring slot `fill`
-    if (s < total) {
-      const bool is_v = s >= n_it;
-      const int j = min(jt + (is_v ? s - n_it : s) * kStep, T - 1);
-      cross_cp16(ring + fill * kCrossThreads + tid, kbase + (is_v ? d : 0) + j * ld);
-    }
-    cross_commit();  // (an empty group keeps the count uniform)
+  // byte pointers: this thread's 16 bytes of row jt (K half); rows of later iterations are `stepb` apart, V is `k2v` on
+  const unsigned char* kp = reinterpret_cast<const unsigned char*>(cross_kv + (long long)slot[b] * seq_stride + (long long)jt * ld +
+                                                                   h * kHd + sub * 8);
+  const long long stepb = (long long)kStep * ld * 2, k2v = (long long)d * 2;
+  const int j_last = jt + (n_it - 1) * kStep;  // row of the last iteration: past the end for some warps when T % 32 != 0
+  const long long fix = j_last >= T ? (long long)(T - 1 - j_last) * ld * 2 : 0;  // ... those re-read row T - 1 instead
+  auto request = [&](const unsigned char* src, int pos) {
+    cross_cp16(ring + (pos & (kRing - 1)) * kCrossThreads, src);
+    cross_commit();
   };
+  auto take = [&](int pos) -> uint4 {  // (before this iteration's request: kRing - 1 + pos groups are committed)
+    cross_wait<kRing - 2>();
+    return ring[(pos & (kRing - 1)) * kCrossThreads];
+  };
+  const unsigned char* rq = kp;
 #pragma unroll
-  for (int s = 0; s < kRing - 1; ++s) request(s, s);
+  for (int s = 0; s < kRing - 1; ++s) {
+    request(rq, s);
+    rq += stepb;
+  }
 
   float qv[8];
   if (n_split > 0) {
@@ -920,51 +941,55 @@ decoder_cross_attention_ring_kernel(int n_head, const __nv_bfloat16* __restrict_
 #pragma unroll
     for (int i = 0; i < 8; ++i) qv[i] = __bfloat162float(__float2bfloat16(qv[i])) * c;
   } else {
-    const uint4 u = *reinterpret_cast<const uint4*>(q + (long long)b * d + h * kHd + sub * 8);
-    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+    float f[8];
+    cross_unpack8(*reinterpret_cast<const uint4*>(q + (long long)b * d + h * kHd + sub * 8), f);
     const float c = 0.125f * kLog2e;
-    qv[0] = a0.x * c; qv[1] = a0.y * c; qv[2] = a1.x * c; qv[3] = a1.y * c;
-    qv[4] = a2.x * c; qv[5] = a2.y * c; qv[6] = a3.x * c; qv[7] = a3.y * c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = f[i] * c;
   }
-
-  int cons = 0, fill = kRing - 1;  // slot to consume; slot to refill (the one consumed an iteration ago)
-  auto next = [&](int s) -> uint4 {  // the row at stream position s; requests position s + kRing - 1
-    cross_wait<kRing - 2>();
-    const uint4 u = ring[cons * kCrossThreads + tid];
-    request(s + kRing - 1, fill);
-    fill = cons;
-    cons = (cons + 1 == kRing) ? 0 : cons + 1;
-    return u;
-  };
 
   // ---- scores ----
   float mx = -INFINITY;
-  for (int i = 0; i < n_it; ++i) {
-    const uint4 u = next(i);
-    const int j = jt + i * kStep;
-    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-    float s = a0.x * qv[0];
-    s = fmaf(a0.y, qv[1], s);
-    s = fmaf(a1.x, qv[2], s);
-    s = fmaf(a1.y, qv[3], s);
-    s = fmaf(a2.x, qv[4], s);
-    s = fmaf(a2.y, qv[5], s);
-    s = fmaf(a3.x, qv[6], s);
-    s = fmaf(a3.y, qv[7], s);
+  float* sp = s_p + jt;  // (sub == 0 lanes write)
+  const bool writer = sub == 0;
+  auto score = [&](const uint4& u, int i) {
+    float f[8];
+    cross_unpack8(u, f);
+    float s = f[0] * qv[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) s = fmaf(f[e], qv[e], s);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (j < T) {
-      if (sub == 0) s_p[j] = s;
-      mx = fmaxf(mx, s);
-    }
+    if (writer) sp[i * kStep] = s;  // rows past T are copies of row T - 1: harmless for the maximum, zeroed below
+    mx = fmaxf(mx, s);
+  };
+  int i = 0;
+  for (; i < n_it - kRing; ++i) {  // requests: K rows up to the second to last
+    const uint4 u = take(i);
+    request(rq, i + kRing - 1);
+    rq += stepb;
+    score(u, i);
+  }
+  {  // request: the last K row (clamped); from here on V
+    const uint4 u = take(i);
+    request(rq + fix, i + kRing - 1);
+    rq = kp + k2v;
+    score(u, i);
+    ++i;
+  }
+  for (; i < n_it; ++i) {  // requests: the first kRing - 1 V rows, in flight across the softmax barriers
+    const uint4 u = take(i);
+    request(rq, i + kRing - 1);
+    rq += stepb;
+    score(u, i);
   }
   mx = warp_max(mx);
   if (lane == 0) s_red[warp] = mx;
   __syncthreads();
   mx = s_red[0];
 #pragma unroll
-  for (int i = 1; i < kCrossWarps; ++i) mx = fmaxf(mx, s_red[i]);
+  for (int w = 1; w < kCrossWarps; ++w) mx = fmaxf(mx, s_red[w]);
   __syncthreads();
   float sum = 0.0f;
   for (int j = tid; j < T; j += kCrossThreads) {
@@ -972,39 +997,51 @@ decoder_cross_attention_ring_kernel(int n_head, const __nv_bfloat16* __restrict_
     sum += p;
     s_p[j] = __bfloat162float(__float2bfloat16(p));  // bf16 probabilities, as in the tensor-core path
   }
+  if (tid < n_it * kStep - T) s_p[T + tid] = 0.0f;  // padding keys carry no weight
   sum = warp_sum(sum);
   if (lane == 0) s_red[warp] = sum;
   __syncthreads();
   sum = 0.0f;
 #pragma unroll
-  for (int i = 0; i < kCrossWarps; ++i) sum += s_red[i];
+  for (int w = 0; w < kCrossWarps; ++w) sum += s_red[w];
 
   // ---- output ----
   float acc[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-  for (int i = 0; i < n_it; ++i) {
-    const uint4 u = next(n_it + i);
-    const int j = jt + i * kStep;
-    const float p = (j < T) ? s_p[j] : 0.0f;
-    const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-    acc[0] = fmaf(p, a0.x, acc[0]);
-    acc[1] = fmaf(p, a0.y, acc[1]);
-    acc[2] = fmaf(p, a1.x, acc[2]);
-    acc[3] = fmaf(p, a1.y, acc[3]);
-    acc[4] = fmaf(p, a2.x, acc[4]);
-    acc[5] = fmaf(p, a2.y, acc[5]);
-    acc[6] = fmaf(p, a3.x, acc[6]);
-    acc[7] = fmaf(p, a3.y, acc[7]);
+  for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+  auto accumulate = [&](const uint4& u, int k) {
+    const float p = sp[k * kStep];
+    float f[8];
+    cross_unpack8(u, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, f[e], acc[e]);
+  };
+  int k = 0;
+  for (; k < n_it - kRing; ++k) {
+    const uint4 u = take(n_it + k);
+    request(rq, n_it + k + kRing - 1);
+    rq += stepb;
+    accumulate(u, k);
+  }
+  {
+    const uint4 u = take(n_it + k);
+    request(rq + fix, n_it + k + kRing - 1);  // the last V row
+    accumulate(u, k);
+    ++k;
+  }
+  for (; k < n_it; ++k) {
+    const uint4 u = take(n_it + k);
+    cross_commit();  // (an empty group keeps the wait count uniform)
+    accumulate(u, k);
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  for (int e = 0; e < 8; ++e) {
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
   }
   if (kg == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s_part[warp][sub * 8 + i] = acc[i];
+    for (int e = 0; e < 8; ++e) s_part[warp][sub * 8 + e] = acc[e];
   }
   __syncthreads();
   if (tid < kHd) {
@@ -1042,7 +1079,7 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
   const int kv_splits = (kv_part != nullptr && kv_cnt != nullptr && probs_out == nullptr) ? cross_attention_kv_splits(n_seq, n_q, n_head) : 1;
   ProfScope prof_("decoder_cross_attention", stream);
-  if (kv_splits == 1 && probs_out == nullptr && n_q == 1 && cross_ring_enabled()) {
+  if (kv_splits == 1 && probs_out == nullptr && n_q == 1 && T >= kRing * kCrossWarps * 4 && cross_ring_enabled()) {
     B200W_CUDA_OK(launch_k(decoder_cross_attention_ring_kernel, dim3(1, n_head, n_seq), dim3(kCrossThreads), (size_t)kCrossRingSmem,
                            stream, n_head, cross_kv, seq_stride, T, slot, out, q, part, n_split, split_stride, bias, finished));
     count_launch();
