@@ -53,7 +53,7 @@ constexpr int kMiscBt = 512;     // [B][kSmMaxPages] int
 constexpr int kSmBiasMax = 48;
 constexpr int kMiscProf = 680;   // [8] long long (development aid)
 constexpr int kMiscBars = 992;   // mbarriers: last 128 bytes
-static_assert(kSmallMaxBatch * kSmWarps <= kMiscPart && kMiscPart + 2 * 4 * 4 * kSmallMaxBatch <= kMiscAttRed &&
+static_assert(kMiscAttRed + 2 * kSmWarps <= kMiscXown && kSmallMaxBatch * kSmWarps <= kMiscPart && kMiscPart + 2 * 4 * 4 * kSmallMaxBatch <= kMiscAttRed &&
               kMiscAttRed + kSmWarps <= kMiscXown && kMiscXown + kSmallMaxBatch * kSmOwnMax <= kMiscKvRow &&
               kMiscKvRow + 2 * kSmallMaxBatch <= kMiscBias && kMiscBias + kSmBiasMax <= kMiscBt &&
               kMiscBt + kSmallMaxBatch * kSmMaxPages <= kMiscBars, "misc layout");
@@ -183,6 +183,44 @@ __device__ __forceinline__ void sm_dot1(const uint4* __restrict__ wp, const __nv
 #pragma unroll
     for (int b = 0; b < B; ++b) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
   }
+}
+
+// B == 1: the lane's 8 * S activation values stay in registers (as f32) for all rows of a phase -- every row of every
+// stage multiplies the same elements, so the 2 * S shared-memory loads and 8 * S unpack instructions per row shrink to
+// S loads and 8 * S unpacks of the weights alone.
+template <int S>
+__device__ __forceinline__ void sm_load_x(const __nv_bfloat16* __restrict__ act, int lane, float (&xr)[S * 8]) {
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    float f[8];
+    sm_unpack8(*reinterpret_cast<const uint4*>(act + i * 256 + lane * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xr[i * 8 + e] = f[e];
+  }
+}
+template <int S>
+__device__ __forceinline__ float sm_dot1_reg(const uint4* __restrict__ wp, const float (&xr)[S * 8], int lane) {
+  uint4 w[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i) w[i] = wp[i * 32 + lane];
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    float wf[8];
+    sm_unpack8(w[i], wf);
+    s0 = fmaf(wf[0], xr[i * 8 + 0], s0);
+    s1 = fmaf(wf[1], xr[i * 8 + 1], s1);
+    s2 = fmaf(wf[2], xr[i * 8 + 2], s2);
+    s3 = fmaf(wf[3], xr[i * 8 + 3], s3);
+    s0 = fmaf(wf[4], xr[i * 8 + 4], s0);
+    s1 = fmaf(wf[5], xr[i * 8 + 5], s1);
+    s2 = fmaf(wf[6], xr[i * 8 + 6], s2);
+    s3 = fmaf(wf[7], xr[i * 8 + 7], s3);
+  }
+  float acc = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
 }
 
 struct SmCtx {
@@ -364,6 +402,8 @@ __device__ __forceinline__ void sm_gemv_chunks(SmCtx& c, int N, int K, int epi, 
   float* part = c.s_misc + kMiscPart;  // [2][4 rows][4 parts][B]: double-buffered by chunk parity
   const float* s_bias = c.s_misc + kMiscBias;
   int parity = 0;
+  float xr[B == 1 ? S * 8 : 1];
+  if constexpr (B == 1) sm_load_x<S>(c.act + kpart * klen, c.lane, xr);
   for (int r = n0; r < n1; r += R) {
     const int rows = min(R, n1 - r);
     const bool mine_row = row_in < rows;
@@ -374,7 +414,8 @@ __device__ __forceinline__ void sm_gemv_chunks(SmCtx& c, int N, int K, int epi, 
     float acc[B];
     if (mine_row) {
       const unsigned char* wrow = c.ring + c.rg.stage * kSmStageBytes + ((size_t)row_in * K + (size_t)kpart * klen) * 2;
-      sm_dot1<B, S>(reinterpret_cast<const uint4*>(wrow), c.act + kpart * klen, K, c.lane, acc);
+      if constexpr (B == 1) acc[0] = sm_dot1_reg<S>(reinterpret_cast<const uint4*>(wrow), xr, c.lane);
+      else sm_dot1<B, S>(reinterpret_cast<const uint4*>(wrow), c.act + kpart * klen, K, c.lane, acc);
     }
     __syncwarp();
     if (c.lane == 0) mbar_arrive(&c.empty[c.rg.stage]);  // the stage can be refilled while the results are written
