@@ -90,6 +90,21 @@ static bool absorb_enabled() {
 }
 constexpr int kAbsorbMinBatch = 16;
 
+// Experiment (tools/time_dual_eager.py): two half-batches on two streams in anti-phase -- the cross-attention launches of
+// the two halves are chained by events (A.l -> B.l -> A.l+1 ...), so that while one half streams its K / V the other
+// half runs its latency-bound chains and self-attention.  role -1: off.
+static int g_cross_role = -1;
+static cudaEvent_t g_cross_ev[2][64];
+static bool g_cross_ev_ready = false, g_cross_ev_recorded[2] = {false, false};
+static int cross_events_ready() {
+  if (!g_cross_ev_ready) {
+    for (int r = 0; r < 2; ++r)
+      for (int i = 0; i < 64; ++i) B200W_CUDA_OK(cudaEventCreateWithFlags(&g_cross_ev[r][i], cudaEventDisableTiming));
+    g_cross_ev_ready = true;
+  }
+  return kOk;
+}
+
 // B200W_CHAIN=0 runs every small-M phase of a decode step as its own launch (the pre-chain path, kept for A/B)
 static bool chain_enabled() {
   static int v = -1;
@@ -840,10 +855,22 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
         B200W_TRY(launch_absorbed_cross_attention(bf.part_q, sp_d, s1, L.b_cq, nullptr, B, H, L.w_ckv, L.b_ckv,
                                                   static_cast<const __nv_bfloat16*>(st->xa), st->xa_slots, T, st->cross_slot,
                                                   done, bf.absorb_ws, (__nv_bfloat16*)bf.att, stream));
-      else
+      else {
+        const int role = g_cross_role, nl = dm.n_text_layer;
+        if (role >= 0 && nl <= 64) {
+          B200W_TRY(cross_events_ready());
+          if (role == 0 && l > 0) B200W_CUDA_OK(cudaStreamWaitEvent(stream, g_cross_ev[1][l - 1], 0));
+          if (role == 0 && l == 0 && g_cross_ev_recorded[1]) B200W_CUDA_OK(cudaStreamWaitEvent(stream, g_cross_ev[1][nl - 1], 0));
+          if (role == 1) B200W_CUDA_OK(cudaStreamWaitEvent(stream, g_cross_ev[0][l], 0));
+        }
         B200W_TRY(launch_decoder_cross_attention(nullptr, B, 1, H, ckv, (long long)T * 2 * d, T, st->cross_slot,
                                                  (__nv_bfloat16*)bf.att, stream, bf.part_q, sp_d, s1, L.b_cq, done, nullptr, kvp,
                                                  kvc));
+        if (role >= 0 && nl <= 64) {
+          B200W_CUDA_OK(cudaEventRecord(g_cross_ev[role][l], stream));
+          g_cross_ev_recorded[role] = true;
+        }
+      }
       {
         const bool last = l + 1 == dm.n_text_layer;
         ChainMaps maps;
@@ -1066,6 +1093,8 @@ int b200w_debug_read_stream(const void* buf, size_t bytes, void* sink, void* str
                          static_cast<const uint4*>(buf), bytes / 16, static_cast<unsigned long long*>(sink)));
   return kOk;
 }
+
+void b200w_debug_cross_role(int role) { g_cross_role = role; }
 
 // n_phases - 1 grid barriers and nothing else
 int b200w_debug_chain_barriers(int n_phases, unsigned int* counter, float* x, void* h, const float* gamma, void* stream) {

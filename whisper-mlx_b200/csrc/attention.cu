@@ -11,6 +11,7 @@
 // K7 decoder self-attention over the paged KV cache (q-len 1, or a short prompt), CUDA cores.
 // K8 decoder cross-attention (S = 1500), the HBM-bound hot spot of decoding: 16-byte coalesced loads,
 //    8 lanes per key row, each K/V byte read exactly once per step.
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -1052,6 +1053,201 @@ decoder_cross_attention_ring_kernel(int n_head, const __nv_bfloat16* __restrict_
   }
 }
 
+// K8p: the form for two half-batches decoded on two streams (B200W_DECODE_STREAMS=2): ONE persistent CTA per SM that
+// leaves room for a co-resident decode-chain CTA of the other half-batch (K11: 43 K registers).  512 threads at <= 40
+// registers, a ring of kRingP x 16 B per thread (64 KB in flight per SM), (sequence, head) units dealt round-robin and
+// walked back to back: the request stream runs ahead across the K -> V switch AND across unit boundaries, so the SM's
+// bytes in flight never drain.  Queries of all of a CTA's units are reduced once, at the start of the launch.
+constexpr int kCrossPThreads = 512;
+constexpr int kCrossPWarps = kCrossPThreads / 32;
+constexpr int kRingP = 8;
+constexpr int kCrossPSmem = kRingP * kCrossPThreads * 16;
+constexpr int kCrossPMaxUnits = 24;  // units per CTA (round-robin): n_seq * n_head <= 24 * grid
+
+__global__ void __launch_bounds__(kCrossPThreads, 3)
+decoder_cross_attention_persistent_kernel(int n_head, int n_units, const __nv_bfloat16* __restrict__ cross_kv, long long seq_stride,
+                                          int T, const int* __restrict__ slot, __nv_bfloat16* __restrict__ out,
+                                          const __nv_bfloat16* __restrict__ q, const float* __restrict__ part, int n_split,
+                                          long long split_stride, const float* __restrict__ bias, const int* __restrict__ finished) {
+  extern __shared__ __align__(16) unsigned char cross_ring_raw[];
+  uint4* ring = reinterpret_cast<uint4*>(cross_ring_raw) + threadIdx.x;
+  __shared__ float s_p[kMaxCrossKeys];
+  __shared__ float s_red[kCrossPWarps];
+  __shared__ float s_part[kCrossPWarps][kHd];
+  __shared__ __align__(16) float s_q[kCrossPMaxUnits][kHd];  // scaled queries of this CTA's units
+  __shared__ long long s_base[kCrossPMaxUnits + 1];          // byte offset of a unit's first K row (this CTA's list)
+  __shared__ int s_unit[kCrossPMaxUnits];
+  __shared__ int s_n;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane & 7, kg = lane >> 3;
+  const int d = n_head * kHd;
+  const long long ld = 2ll * d;
+  pdl_wait();
+  pdl_launch_dependents();
+  // this CTA's units (sequences that have emitted EOT are skipped)
+  if (tid == 0) {
+    int n = 0;
+    for (int u = blockIdx.x; u < n_units && n < kCrossPMaxUnits; u += gridDim.x) {
+      const int b = u / n_head, h = u - b * n_head;
+      if (finished != nullptr && finished[b]) continue;
+      s_unit[n] = u;
+      s_base[n] = ((long long)slot[b] * seq_stride + h * kHd) * 2;
+      ++n;
+    }
+    s_base[n] = n > 0 ? s_base[n - 1] : 0;  // (the request stream may look one unit past the end; never dereferenced)
+    s_n = n;
+  }
+  __syncthreads();
+  const int n_mine = s_n;
+  if (n_mine == 0) return;
+  constexpr int kStep = kCrossPWarps * 4;
+  const int n_it = (T + kStep - 1) / kStep;  // >= kRingP (checked by the launcher)
+  const int jt = warp * 4 + kg;
+  const unsigned char* kv0 = reinterpret_cast<const unsigned char*>(cross_kv) + ((long long)jt * ld + sub * 8) * 2;
+  const long long stepb = (long long)kStep * ld * 2, k2v = (long long)d * 2;
+  const int j_last = jt + (n_it - 1) * kStep;
+  const long long fix = j_last >= T ? (long long)(T - 1 - j_last) * ld * 2 : 0;
+  // request stream: unit ru, pass (0 = K, 1 = V), iteration ri
+  int ru = 0, ri = 0, rpass = 0;
+  const unsigned char* rq = kv0 + s_base[0];
+  int rpos = 0;  // ring position of the next request (== number of requests issued)
+  auto request = [&]() {
+    if (ru < n_mine) {
+      cross_cp16(ring + (rpos & (kRingP - 1)) * kCrossPThreads, ri == n_it - 1 ? rq + fix : rq);
+      rq += stepb;
+      if (++ri == n_it) {
+        ri = 0;
+        if (rpass == 0) {
+          rpass = 1;
+          rq = kv0 + s_base[ru] + k2v;
+        } else {
+          rpass = 0;
+          ++ru;
+          rq = kv0 + s_base[ru];
+        }
+      }
+    }
+    cross_commit();
+    ++rpos;
+  };
+#pragma unroll
+  for (int s = 0; s < kRingP - 1; ++s) request();
+  // queries of all units of this CTA: one (unit, dim) per thread and round
+  for (int i = tid; i < n_mine * kHd; i += kCrossPThreads) {
+    const int k = i >> 6, e = i & 63, u = s_unit[k];
+    const int b = u / n_head, h = u - b * n_head;
+    float v;
+    if (n_split > 0) {
+      v = bias[h * kHd + e];
+      for (int sidx = 0; sidx < n_split; ++sidx) v += part[sidx * split_stride + (long long)b * d + h * kHd + e];
+      v = __bfloat162float(__float2bfloat16(v));
+    } else {
+      v = __bfloat162float(q[(long long)b * d + h * kHd + e]);
+    }
+    s_q[k][e] = v * (0.125f * kLog2e);
+  }
+  __syncthreads();
+
+  int cpos = 0;  // ring position of the next row to consume
+  auto take = [&]() -> uint4 {
+    cross_wait<kRingP - 2>();
+    const uint4 u = ring[(cpos & (kRingP - 1)) * kCrossPThreads];
+    ++cpos;
+    return u;
+  };
+  float* sp = s_p + jt;
+  const bool writer = sub == 0;
+  for (int k = 0; k < n_mine; ++k) {
+    float qv[8];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(&s_q[k][sub * 8]), e = *reinterpret_cast<const float4*>(&s_q[k][sub * 8 + 4]);
+      qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = e.x; qv[5] = e.y; qv[6] = e.z; qv[7] = e.w;
+    }
+    float mx = -INFINITY;
+    for (int i = 0; i < n_it; ++i) {
+      const uint4 u = take();
+      request();
+      float f[8];
+      cross_unpack8(u, f);
+      float s = f[0] * qv[0];
+#pragma unroll
+      for (int e = 1; e < 8; ++e) s = fmaf(f[e], qv[e], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (writer) sp[i * kStep] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kCrossPWarps; ++w) mx = fmaxf(mx, s_red[w]);
+    __syncthreads();
+    float sum = 0.0f;
+    for (int j = tid; j < T; j += kCrossPThreads) {
+      const float p = fast_exp2(s_p[j] - mx);
+      sum += p;
+      s_p[j] = __bfloat162float(__float2bfloat16(p));
+    }
+    if (tid < n_it * kStep - T) s_p[T + tid] = 0.0f;
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    sum = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kCrossPWarps; ++w) sum += s_red[w];
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    for (int i = 0; i < n_it; ++i) {
+      const uint4 u = take();
+      request();
+      const float p = sp[i * kStep];
+      float f[8];
+      cross_unpack8(u, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, f[e], acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    if (kg == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s_part[warp][sub * 8 + e] = acc[e];
+    }
+    __syncthreads();  // every warp has left the V pass: s_p may be rewritten by the next unit's scores
+    if (tid < kHd) {
+      float v = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kCrossPWarps; ++w) v += s_part[w][tid];
+      const int u = s_unit[k];
+      out[(long long)(u / n_head) * d + (u % n_head) * kHd + tid] = __float2bfloat16(v / sum);
+    }
+  }
+}
+
+// B200W_CROSS_PERSIST=1: the persistent one-CTA-per-SM form (K8p) for full batches
+static bool cross_persist_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200W_CROSS_PERSIST");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    if (v) v = cudaFuncSetAttribute(decoder_cross_attention_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrossPSmem) == cudaSuccess ? 1 : 0;
+    // the same shared-memory carve-out as the chain kernel it is meant to share SMs with (an SM is drained before its
+    // carve-out changes): this kernel, and the self-attention that runs beside it on the other stream
+    if (v) {
+      cudaFuncSetAttribute(decoder_cross_attention_persistent_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(decoder_self_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+  }
+  return v != 0;
+}
+
 // B200W_CROSS_STREAM=0 keeps the register-staged K8 for every shape (A/B)
 static bool cross_ring_enabled() {
   static int v = -1;
@@ -1079,6 +1275,14 @@ int launch_decoder_cross_attention(const __nv_bfloat16* q, int n_seq, int n_q, i
   B200W_CHECK_ARG(T > 0 && T <= kMaxCrossKeys, "cross_attention: T above %d", kMaxCrossKeys);
   const int kv_splits = (kv_part != nullptr && kv_cnt != nullptr && probs_out == nullptr) ? cross_attention_kv_splits(n_seq, n_q, n_head) : 1;
   ProfScope prof_("decoder_cross_attention", stream);
+  if (kv_splits == 1 && probs_out == nullptr && n_q == 1 && T >= kRingP * kCrossPWarps * 4 && cross_persist_enabled() &&
+      n_seq * n_head <= kCrossPMaxUnits * device_sm_count()) {
+    B200W_CUDA_OK(launch_k(decoder_cross_attention_persistent_kernel, dim3(std::min(device_sm_count(), n_seq * n_head)),
+                           dim3(kCrossPThreads), (size_t)kCrossPSmem, stream, n_head, n_seq * n_head, cross_kv, seq_stride, T, slot, out,
+                           q, part, n_split, split_stride, bias, finished));
+    count_launch();
+    return kOk;
+  }
   if (kv_splits == 1 && probs_out == nullptr && n_q == 1 && T >= kRing * kCrossWarps * 4 && cross_ring_enabled()) {
     B200W_CUDA_OK(launch_k(decoder_cross_attention_ring_kernel, dim3(1, n_head, n_seq), dim3(kCrossThreads), (size_t)kCrossRingSmem,
                            stream, n_head, cross_kv, seq_stride, T, slot, out, q, part, n_split, split_stride, bias, finished));

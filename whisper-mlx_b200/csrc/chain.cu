@@ -20,7 +20,10 @@ constexpr int kChBM = 128;
 constexpr int kChBN = 64;
 constexpr int kChBK = 64;
 constexpr int kChThreads = 384;  // 4 role warps + 8 epilogue warps (the K5 layout)
-constexpr int kChStages = 8;
+#ifndef B200W_CHAIN_STAGES
+#define B200W_CHAIN_STAGES 8
+#endif
+constexpr int kChStages = B200W_CHAIN_STAGES;
 constexpr int kChABytes = kChBM * kChBK * 2;
 constexpr int kChBBytes = kChBN * kChBK * 2;
 constexpr int kChStageBytes = kChABytes + kChBBytes;
@@ -382,6 +385,9 @@ int init_chain() {
   if (done) return kOk;
   B200W_CUDA_OK(cudaFuncSetAttribute(decode_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes));
   B200W_CUDA_OK(cudaFuncSetAttribute(decode_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmemBytes));
+  // the largest shared-memory carve-out whatever kChStages is: kernels that are to share an SM need the SAME carve-out
+  cudaFuncSetAttribute(decode_chain_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(decode_chain_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   // B200W_CHAIN_MC=1 opts into the cluster-multicast form.  Measured on B200 (large-v3, 120 sequences): 7.46 ms per step
   // against 7.44 ms without it -- only 33 clusters of 4 fit at once (132 of 148 SMs), the four CTAs of a cluster advance
   // in lockstep, and a phase is dominated by its fixed ~4.5 us, not by operand ingest.  Off by default.
@@ -493,6 +499,10 @@ int launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t strea
   attr[1].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = mc ? 2 : 1;
+  // B200W_CHAIN_NONCOOP=1 (experiment): a plain launch -- co-residency of the 148 CTAs is then only what the sizes of the
+  // kernels sharing the GPU make it (one CTA per SM by shared memory); a barrier that cannot complete traps
+  static const bool noncoop = [] { const char* e = getenv("B200W_CHAIN_NONCOOP"); return e != nullptr && e[0] == '1'; }();
+  if (noncoop && !mc) cfg.numAttrs = 0;
   ProfScope prof_("dec_chain", stream);
   ChainParams pl = p;
   pl.timeline = nullptr;
