@@ -259,7 +259,7 @@ def kernel_rooflines(model, peaks, n_windows: int, with_logmel: bool = True):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one decoder_cross_attention_ring_kernel launch at 120 windows (ncu --set full)
-CROSS_DRAM_BYTES_AT_120 = 921_940_480 + 4_274_944
+CROSS_DRAM_BYTES_AT_120 = 921_962_496 + 4_662_528
 
 # FP32-issue ceiling of the log-mel kernel: warp-instructions per frame from the ncu source view of the shipped kernel
 # (profiles/) against 4 warp-instructions per clock per SM on 148 SMs

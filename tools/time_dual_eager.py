@@ -58,4 +58,26 @@ for mode in ("free", "antiphase", "free", "antiphase"):
     role(-1)
     torch.cuda.synchronize()
     out.setdefault("two_streams_" + mode + "_ms", []).append(round((time.perf_counter() - t0) / a.steps * 1e3, 3))
+# per-kernel times (CUDA events around every launch of the library) of one stream alone and of the anti-phase pair
+from whisper_mlx_b200._lib import kernel_profile
+
+
+def shares(prof):
+    return {k: round(v["total_ms"] / v["launches"] * 1e3, 1) for k, v in prof.result.items() if k in ("dec_chain", "decoder_self_attention", "decoder_cross_attention")}
+
+
+with kernel_profile() as prof:
+    with torch.cuda.stream(streams[0]):
+        eager_step(halves[0])
+    torch.cuda.synchronize()
+out["half_batch_alone_avg_us"] = shares(prof)
+with kernel_profile() as prof:
+    for _ in range(2):
+        for i in (0, 1):
+            role(i)
+            with torch.cuda.stream(streams[i]):
+                eager_step(halves[i])
+    role(-1)
+    torch.cuda.synchronize()
+out["antiphase_avg_us"] = shares(prof)
 print(json.dumps(out))
