@@ -30,6 +30,22 @@ __device__ __forceinline__ float fast_exp2(float x) {
 #endif
 }
 
+// thread-private cp.async rings of the decode attention kernels (K7r, K8r, K8p)
+__device__ __forceinline__ void cross_cp16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cross_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cross_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// eight bf16 -> f32 with one integer instruction each (shift / mask)
+__device__ __forceinline__ void cross_unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+
 // exp2 on the FMA / ALU pipes (Cody-Waite: round to the nearest integer with the 1.5 * 2^23 trick, cubic minimax of 2^f on
 // [-0.5, 0.5], integer added into the exponent field): relative error <= 7.5e-5, invisible after the bf16 rounding of P.
 // FlashAttention-4's software exp2 for a share of the probabilities: 9 FMA / ALU instructions at 128 lanes per clock against
@@ -608,6 +624,169 @@ decoder_self_attention_kernel(const __nv_bfloat16* __restrict__ qkv, int n_seq, 
   }
 }
 
+// K7r: the decode-step form (n_q == 1, q | k | v as split-K slabs) with the cached rows streamed through a thread-private
+// cp.async ring like K8r: one page-table entry (staged in shared memory) per request, K rows then V rows in one
+// continuous stream that starts while warp 0 still reduces this token's q | k | v.  K7 issues a sweep of 8 loads per
+// thread, waits, computes: at 200 cached keys its marginal bandwidth was 3.1 TB/s.
+#ifndef B200W_SELF_RING
+#define B200W_SELF_RING 8
+#endif
+#ifndef B200W_SELF_RING_CTAS
+#define B200W_SELF_RING_CTAS 8
+#endif
+constexpr int kSelfRing = B200W_SELF_RING;  // a power of two
+constexpr int kSelfMaxPages = 64;
+
+__global__ void __launch_bounds__(kSelfThreads, B200W_SELF_RING_CTAS)
+decoder_self_attention_ring_kernel(int n_head, const int* __restrict__ pos, __nv_bfloat16* k_pages, __nv_bfloat16* v_pages,
+                                   const int* __restrict__ block_table, int max_pages, int page_size, __nv_bfloat16* __restrict__ out,
+                                   const float* __restrict__ part, int n_split, long long split_stride, const float* __restrict__ bias,
+                                   const int* __restrict__ finished) {
+  __shared__ __align__(16) uint4 s_ring[kSelfRing][kSelfThreads];
+  __shared__ float s_p[kMaxSelfKeys + 16];
+  __shared__ float s_red[kSelfWarps];
+  __shared__ float s_part[kSelfWarps][kHd];
+  __shared__ uint4 s_qkv[3][8];  // this token's q, k, v of the head (bf16), 8 dims per entry
+  __shared__ int s_bt[kSelfMaxPages];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x % n_head, b = blockIdx.x / n_head;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (finished != nullptr && finished[b]) return;
+  const int sub = lane & 7, kg = lane >> 3;
+  const int d = n_head * kHd;
+  const int p0 = pos[b], n_keys = p0 + 1;
+  const int pshift = __ffs(page_size) - 1;
+  for (int i = tid; i < max_pages; i += kSelfThreads) s_bt[i] = block_table[b * max_pages + i];
+  __syncthreads();
+  constexpr int kStep = kSelfWarps * 4;
+  const int n_it = (n_keys + kStep - 1) / kStep, total = 2 * n_it;
+  const int jt = warp * 4 + kg;
+  const long long col = (long long)h * kHd + sub * 8;
+  uint4* ring = &s_ring[0][tid];
+  auto request = [&](int s) {
+    if (s < total) {
+      const bool is_v = s >= n_it;
+      const int j = min(jt + (is_v ? s - n_it : s) * kStep, n_keys - 1);
+      const long long row = (long long)s_bt[j >> pshift] * page_size + (j & (page_size - 1));
+      cross_cp16(ring + (s & (kSelfRing - 1)) * kSelfThreads, (is_v ? v_pages : k_pages) + row * d + col);
+    }
+    cross_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kSelfRing - 1; ++s) request(s);
+  // this token's q | k | v: warp 0, lanes 0-7 reduce q, 8-15 k, 16-23 v; k / v are appended to the paged cache (the
+  // stream's own read of that row is ignored: the row is taken from shared memory)
+  if (warp == 0 && kg < 3) {
+    float v8[8];
+    const long long c3 = (long long)kg * d + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = bias[c3 + i];
+    for (int sidx = 0; sidx < n_split; ++sidx) {
+      const float* pp = part + sidx * split_stride + (long long)b * 3 * d + c3;
+      const float4 a0 = *reinterpret_cast<const float4*>(pp), a1 = *reinterpret_cast<const float4*>(pp + 4);
+      v8[0] += a0.x; v8[1] += a0.y; v8[2] += a0.z; v8[3] += a0.w;
+      v8[4] += a1.x; v8[5] += a1.y; v8[6] += a1.z; v8[7] += a1.w;
+    }
+    const uint4 packed = make_uint4(pack_bf16x2(v8[0], v8[1]), pack_bf16x2(v8[2], v8[3]), pack_bf16x2(v8[4], v8[5]),
+                                    pack_bf16x2(v8[6], v8[7]));
+    s_qkv[kg][sub] = packed;
+    if (kg > 0) {
+      const long long row = (long long)s_bt[p0 >> pshift] * page_size + (p0 & (page_size - 1));
+      *reinterpret_cast<uint4*>((kg == 1 ? k_pages : v_pages) + row * d + col) = packed;
+    }
+  }
+  __syncthreads();
+  float qv[8];
+  {
+    float f[8];
+    cross_unpack8(s_qkv[0][sub], f);
+    const float c = 0.125f * kLog2e;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qv[i] = f[i] * c;
+  }
+  auto take = [&](int s, int j, int which) -> uint4 {
+    cross_wait<kSelfRing - 2>();
+    uint4 u = ring[(s & (kSelfRing - 1)) * kSelfThreads];
+    request(s + kSelfRing - 1);
+    if (j >= p0) u = s_qkv[which][sub];  // this token's row (and the clamped padding rows after it)
+    return u;
+  };
+  float mx = -INFINITY;
+  for (int i = 0; i < n_it; ++i) {
+    const int j = jt + i * kStep;
+    const uint4 u = take(i, j, 1);
+    float f[8];
+    cross_unpack8(u, f);
+    float sc = f[0] * qv[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) sc = fmaf(f[e], qv[e], sc);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+    if (sub == 0) s_p[j] = sc;  // (padding rows repeat the last key: harmless for the maximum, zeroed below)
+    mx = fmaxf(mx, sc);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int i = 1; i < kSelfWarps; ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
+  float sum = 0.0f;
+  for (int j = tid; j < n_keys; j += kSelfThreads) {
+    const float p = fast_exp2(s_p[j] - mx);
+    sum += p;
+    s_p[j] = __bfloat162float(__float2bfloat16(p));  // bf16 probabilities, as in the tensor-core path
+  }
+  if (tid < n_it * kStep - n_keys) s_p[n_keys + tid] = 0.0f;
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kSelfWarps; ++i) sum += s_red[i];
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < n_it; ++i) {
+    const int j = jt + i * kStep;
+    const uint4 u = take(n_it + i, j, 2);
+    const float p = s_p[j];
+    float f[8];
+    cross_unpack8(u, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, f[e], acc[e]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (kg == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_part[warp][sub * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < kHd) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kSelfWarps; ++w) v += s_part[w][tid];
+    out[(long long)b * d + h * kHd + tid] = __float2bfloat16(v / sum);
+  }
+}
+
+// B200W_SELF_STREAM=0 keeps K7 for every shape (A/B)
+static bool self_ring_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200W_SELF_STREAM");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, int n_head, const int* pos,
                                   __nv_bfloat16* k_pages, __nv_bfloat16* v_pages, const int* block_table,
                                   int max_pages_per_seq, int page_size, __nv_bfloat16* out, cudaStream_t stream,
@@ -620,6 +799,12 @@ int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, 
   B200W_CHECK_ARG(page_size > 0 && (page_size & (page_size - 1)) == 0, "self_attention: page_size must be a power of two");
   const int units = n_seq * n_head * n_q;
   ProfScope prof_("decoder_self_attention", stream);
+  if (n_split > 0 && n_q == 1 && max_pages_per_seq <= kSelfMaxPages && self_ring_enabled()) {
+    B200W_CUDA_OK(launch_k(decoder_self_attention_ring_kernel, dim3(units), dim3(kSelfThreads), 0, stream, n_head, pos, k_pages, v_pages,
+                           block_table, max_pages_per_seq, page_size, out, part, n_split, split_stride, bias, finished));
+    count_launch();
+    return kOk;
+  }
   B200W_CUDA_OK(launch_k(decoder_self_attention_kernel, dim3(units), dim3(kSelfThreads), 0, stream,
                          qkv, n_seq, n_q, n_head, pos, k_pages, v_pages, block_table, max_pages_per_seq, page_size, out,
                          part, n_split, split_stride, bias, finished));
@@ -863,20 +1048,6 @@ constexpr int kCrossRingSmem = kRing * kCrossThreads * 16;
 #ifndef B200W_CROSS_RING_CTAS
 #define B200W_CROSS_RING_CTAS 4
 #endif
-
-__device__ __forceinline__ void cross_cp16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cross_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cross_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// eight bf16 -> f32 with one integer instruction each (shift / mask)
-__device__ __forceinline__ void cross_unpack8(const uint4& u, float (&f)[8]) {
-  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
-  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
-  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
-  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
-}
 
 // The kernel issues 58 -> 40 warp-instructions per 512 bytes in this form (ncu r02: the first ring version ran at
 // 78 % issue-active -- co-limited by instruction issue, not only by HBM): the source pointer advances by a constant,
