@@ -194,6 +194,12 @@ __device__ __forceinline__ float uniform_hash(unsigned long long seed, unsigned 
   return ((float)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
 }
 
+// kVec: rows are 16-byte aligned (logits_ld % 4 == 0): a thread loads seven float4 per batch before it looks at any of
+// them -- the scalar form's loads sat behind the filter's branches, one round trip to L2 per element and thread
+// (62 us for 120 sequences of 51866 logits).
+constexpr int kFaBatch = 7;
+constexpr int kFaMaskWords = 2048 + 1;  // vocabularies of up to 65536 ids
+template <bool kVec>
 __global__ void __launch_bounds__(kFaThreads)
 filter_argmax_kernel(const float* __restrict__ logits, const uint32_t* __restrict__ suppress_bits,
                      int* __restrict__ tokens, int* __restrict__ n_tokens, int* __restrict__ pos,
@@ -252,21 +258,121 @@ filter_argmax_kernel(const float* __restrict__ logits, const uint32_t* __restric
     }
     return true;
   };
+  // kVec: the rules above as data -- every rule allows or forbids index RANGES (text ids [t_lo, t_hi), timestamps
+  // [s_lo, s_hi]) except three single ids, which are OR-ed into a shared-memory copy of the suppress mask together with
+  // the ids past the vocabulary.  Per logit the filter is then a bit test and two unsigned range compares instead of
+  // the ~50 compare / select instructions the rule chain compiled to (ncu r02: 64 warp-instructions per logit, the
+  // kernel compute-bound at 58 us for 120 sequences).
+  __shared__ uint32_t s_mask[kVec ? kFaMaskWords : 1];
+  int t_lo = 0, t_w = tb, s_lo = tb, s_w = fp.n_vocab - tb;  // range starts and widths (0: nothing allowed)
+  if constexpr (kVec) {
+    const int n_words = (fp.n_vocab + 31) / 32, n_words4 = (4 * ((fp.n_vocab + 3) / 4) + 31) / 32;
+    for (int i = tid; i < n_words4; i += kFaThreads) {
+      uint32_t w = i < n_words ? __ldg(suppress_bits + i) : 0xffffffffu;
+      if (i == n_words - 1 && (fp.n_vocab & 31)) w |= 0xffffffffu << (fp.n_vocab & 31);  // ids past the vocabulary
+      s_mask[i] = w;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (fp.suppress_blank && at_begin) {
+        s_mask[fp.blank >> 5] |= 1u << (fp.blank & 31);
+        s_mask[fp.eot >> 5] |= 1u << (fp.eot & 31);
+      }
+      if (fp.apply_timestamp_rules) s_mask[fp.no_timestamps >> 5] |= 1u << (fp.no_timestamps & 31);
+    }
+    __syncthreads();
+    if (fp.apply_timestamp_rules) {
+      int t_hi = tb, s_hi = fp.n_vocab - 1;
+      if (last_ts) {
+        if (penult_ts) s_hi = tb - 1;  // no timestamp after a pair
+        else t_lo = fp.eot;            // a lone timestamp is followed by a timestamp or EOT
+      }
+      if (has_ts) s_lo = max(s_lo, ts_floor);
+      if (at_begin) {
+        t_hi = 0;
+        if (fp.max_initial_timestamp_index >= 0) s_hi = min(s_hi, tb + fp.max_initial_timestamp_index);
+      }
+      t_w = max(t_hi - t_lo, 0);
+      s_w = max(s_hi + 1 - s_lo, 0);
+    }
+  }
+  auto allowed4 = [&](int v0, bool (&ok)[4]) {  // four consecutive ids (v0 % 4 == 0) share one word of the mask
+    const uint32_t word = s_mask[v0 >> 5] >> (v0 & 31);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int v = v0 + e;
+      ok[e] = !((word >> e) & 1u) && ((unsigned)(v - t_lo) < (unsigned)t_w || (unsigned)(v - s_lo) < (unsigned)s_w);
+    }
+  };
+  const float4* lg4 = reinterpret_cast<const float4*>(lg);
+  const int n4 = (fp.n_vocab + 3) / 4;
 
   // ---- pass 1: maxima (text / timestamp) and, when sampling, Gumbel-perturbed maxima ----
   const bool sampling = fp.temperature > 0.0f;
   const float inv_t = sampling ? 1.0f / fp.temperature : 1.0f;
   ArgMax mt{-INFINITY, 0x7fffffff}, ms{-INFINITY, 0x7fffffff};    // plain maxima: text, timestamps
   ArgMax gt{-INFINITY, 0x7fffffff}, gs{-INFINITY, 0x7fffffff};    // perturbed maxima
-  for (int v = tid; v < fp.n_vocab; v += kFaThreads) {
-    if (!allowed(v)) continue;
-    const float x = lg[v];
+  float st = 0.0f, ss = 0.0f, rm = -INFINITY;  // kVec: partition sums relative to the thread's running maximum rm
+  auto visit1 = [&](int v, float x) {
     ArgMax cur{x, v};
     if (v < tb) mt = better(mt, cur); else ms = better(ms, cur);
     if (sampling) {
       const float u = uniform_hash(fp.seed, b, n, v);
       ArgMax g{x * inv_t - __logf(-__logf(u)), v};
       if (v < tb) gt = better(gt, g); else gs = better(gs, g);
+    }
+  };
+  if constexpr (kVec) {
+    for (int c0 = tid; c0 < n4; c0 += kFaThreads * kFaBatch) {
+      float4 x[kFaBatch];
+#pragma unroll
+      for (int k = 0; k < kFaBatch; ++k) {
+        const int c = c0 + k * kFaThreads;
+        x[k] = c < n4 ? __ldcg(lg4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < kFaBatch; ++k) {
+        const int c = c0 + k * kFaThreads;
+        if (c >= n4) break;
+        bool ok[4];
+        allowed4(4 * c, ok);
+        const float xv[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+        float m4 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (!ok[e]) continue;
+          const int v = 4 * c + e;
+          // (ids ascend within a thread: a strict > keeps the lowest index among equal values)
+          if (v < tb) {
+            if (xv[e] > mt.v) mt = ArgMax{xv[e], v};
+          } else {
+            if (xv[e] > ms.v) ms = ArgMax{xv[e], v};
+          }
+          if (sampling) {
+            const float u = uniform_hash(fp.seed, b, n, v);
+            ArgMax g{xv[e] * inv_t - __logf(-__logf(u)), v};
+            if (v < tb) gt = better(gt, g); else gs = better(gs, g);
+          }
+          m4 = fmaxf(m4, xv[e]);
+        }
+        if (m4 > -INFINITY) {  // online partition sums: one rescale per chunk
+          const float m_new = fmaxf(rm, m4), sc = __expf(rm - m_new);
+          st *= sc;
+          ss *= sc;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (!ok[e]) continue;
+            const float ex = __expf(xv[e] - m_new);
+            if (4 * c + e < tb) st += ex; else ss += ex;
+          }
+          rm = m_new;
+        }
+      }
+    }
+  } else {
+    for (int v = tid; v < fp.n_vocab; v += kFaThreads) {
+      if (!allowed(v)) continue;
+      visit1(v, lg[v]);
     }
   }
   mt = warp_argmax(mt);
@@ -284,12 +390,17 @@ filter_argmax_kernel(const float* __restrict__ logits, const uint32_t* __restric
   }
   const float M = fmaxf(mt.v, ms.v);
 
-  // ---- pass 2: partition sums ----
-  float st = 0.0f, ss = 0.0f;
-  for (int v = tid; v < fp.n_vocab; v += kFaThreads) {
-    if (!allowed(v)) continue;
-    const float e = __expf(lg[v] - M);
-    if (v < tb) st += e; else ss += e;
+  // ---- partition sums: a second pass (scalar form) or the per-thread online sums brought to the common maximum ----
+  if constexpr (kVec) {
+    const float sc = rm > -INFINITY ? __expf(rm - M) : 0.0f;
+    st *= sc;
+    ss *= sc;
+  } else {
+    for (int v = tid; v < fp.n_vocab; v += kFaThreads) {
+      if (!allowed(v)) continue;
+      const float e = __expf(lg[v] - M);
+      if (v < tb) st += e; else ss += e;
+    }
   }
   st = warp_sum(st);
   ss = warp_sum(ss);
@@ -349,8 +460,13 @@ int launch_filter_argmax(const float* logits, const uint32_t* suppress_bits, int
                          float* sum_logprob, int* finished, int n_seq, const FilterParams& fp, cudaStream_t stream) {
   B200W_CHECK_ARG(n_seq > 0 && fp.n_vocab > 0 && fp.logits_ld >= fp.n_vocab, "filter_argmax: bad sizes");
   ProfScope prof_("filter_argmax", stream);
-  B200W_CUDA_OK(launch_k(filter_argmax_kernel, dim3(n_seq), dim3(kFaThreads), 0, stream, logits, suppress_bits, tokens,
-                         n_tokens, pos, sum_logprob, finished, fp));
+  const bool vec = fp.n_vocab <= 65536 && fp.logits_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && fp.logits_ld >= ((fp.n_vocab + 3) / 4) * 4;
+  if (vec)
+    B200W_CUDA_OK(launch_k(filter_argmax_kernel<true>, dim3(n_seq), dim3(kFaThreads), 0, stream, logits, suppress_bits, tokens,
+                           n_tokens, pos, sum_logprob, finished, fp));
+  else
+    B200W_CUDA_OK(launch_k(filter_argmax_kernel<false>, dim3(n_seq), dim3(kFaThreads), 0, stream, logits, suppress_bits, tokens,
+                           n_tokens, pos, sum_logprob, finished, fp));
   count_launch();
   return kOk;
 }
