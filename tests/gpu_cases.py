@@ -472,6 +472,82 @@ def case_splitk_decode_ops():
     return out
 
 
+def case_ring_attention_edges():
+    """K8r / K7r (decode attention streamed through cp.async rings) at the edges of their index arithmetic: key counts
+    around multiples of the 32-key (cross) / 16-key (self) iteration, the shortest length the ring form takes, the
+    longest the kernels accept, page sizes 8 / 16 / 32, scattered slots and pages -- against torch fp32 attention and
+    against the register-staged K8 / K7 (B200W_CROSS_STREAM=0 / B200W_SELF_STREAM=0), which must agree bit for bit."""
+    L, lib = _lib()
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    H, d = 6, 384
+    prev = {k: os.environ.get(k) for k in ("B200W_CROSS_STREAM", "B200W_SELF_STREAM")}
+    try:
+        # ---- cross attention: more (sequence, head) units than the key-split form takes, so the full-batch forms run
+        B, n_slots = 20, 24
+        for T in (256, 257, 300, 1499, 1500, 1536):
+            slot = torch.randperm(n_slots, generator=g)[:B].to(torch.int32)
+            ckv = _bf16(torch.randn(n_slots, T, 2 * d, generator=g))
+            q = _bf16(torch.randn(B, 1, d, generator=g))
+            q_c, ckv_c, slot_c = q.cuda(), ckv.cuda(), slot.cuda()
+            got = {}
+            for form in ("1", "0"):
+                os.environ["B200W_CROSS_STREAM"] = form
+                o = torch.full((B, 1, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+                L.check(lib.b200w_decoder_cross_attention(L.ptr(q_c), B, 1, H, L.ptr(ckv_c), T * 2 * d, T, L.ptr(slot_c), L.ptr(o), L.stream()))
+                torch.cuda.synchronize()
+                got[form] = o.cpu()
+            kv = ckv[slot.long()].float()
+            ref = _sdpa_ref(q.float(), kv[..., :d], kv[..., d:], H)
+            err = (got["1"].float() - ref).abs().max().item()
+            out[f"cross_T{T}"] = err
+            assert err <= 2e-2, (T, err)
+            assert torch.equal(got["1"], got["0"]), f"K8r differs from K8 at T = {T}"
+        # ---- self attention from split-K slabs: positions around the 16-key iterations and the page boundaries
+        n_sl = 2
+        for ps in (8, 16, 32):
+            max_pages = 448 // ps
+            pos_l = [0, 1, 15, 16, 17, 31, 32, 127, 128, 129, 255, 300, 446, 447]
+            B = len(pos_l)
+            pos = torch.tensor(pos_l, dtype=torch.int32).cuda()
+            bt_tab = torch.randperm(B * max_pages, generator=g).to(torch.int32).view(B, max_pages).contiguous().cuda()
+            kp = _bf16(torch.randn(B * max_pages, ps, d, generator=g)).cuda()
+            vp = _bf16(torch.randn(B * max_pages, ps, d, generator=g)).cuda()
+            bias3 = torch.randn(3 * d, generator=g).cuda()
+            part3 = torch.randn(n_sl, 128, 3 * d, generator=g).cuda()
+            res = {}
+            for form in ("1", "0"):
+                os.environ["B200W_SELF_STREAM"] = form
+                kp1, vp1 = kp.clone(), vp.clone()
+                o = torch.full((B, 1, d), float("nan"), dtype=torch.bfloat16, device="cuda")
+                L.check(lib.b200w_decoder_self_attention_splitk(L.ptr(part3), n_sl, 128 * 3 * d, L.ptr(bias3), B, H, L.ptr(pos), L.ptr(kp1),
+                                                                L.ptr(vp1), L.ptr(bt_tab), max_pages, ps, L.ptr(o), L.stream()))
+                torch.cuda.synchronize()
+                res[form] = (o.cpu(), kp1.cpu(), vp1.cpu())
+            assert torch.equal(res["1"][1], res["0"][1]) and torch.equal(res["1"][2], res["0"][2]), "appended K/V rows differ"
+            assert torch.equal(res["1"][0], res["0"][0]), f"K7r differs from K7 at page size {ps}"
+            # and against fp32 attention over the gathered rows
+            qkv = _bf16((part3[:, :B].sum(0) + bias3).cpu())
+            kpc, vpc, btc = res["1"][1], res["1"][2], bt_tab.cpu()
+            errs = []
+            for b in range(B):
+                n_keys = pos_l[b] + 1
+                rows = [int(btc[b, j // ps]) * ps + j % ps for j in range(n_keys)]
+                k = kpc.view(-1, d)[rows].float()[None]
+                v = vpc.view(-1, d)[rows].float()[None]
+                ref = _sdpa_ref(qkv[b, :d].float()[None, None], k, v, H, causal_offset=pos_l[b])
+                errs.append((res["1"][0][b].float() - ref[0]).abs().max().item())
+            out[f"self_ps{ps}"] = max(errs)
+            assert max(errs) <= 2e-2, (ps, errs)
+    finally:
+        for k, v in prev.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return out
+
+
 # ------------------------------------------------------------------------------------------ K9
 def case_filter_argmax():
     """Every branch of the suppression / timestamp grammar against the oracle's host-side rules."""
@@ -1157,6 +1233,7 @@ CASES = {
     "splitk_decode_ops": case_splitk_decode_ops,
     "absorbed_cross_attention": case_absorbed_cross_attention,
     "logmel_pcm16": case_logmel_pcm16,
+    "ring_attention_edges": case_ring_attention_edges,
     "filter_argmax": case_filter_argmax,
     "sampling_distribution": case_sampling_distribution,
     "encoder_tiny": case_encoder_tiny,

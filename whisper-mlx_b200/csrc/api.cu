@@ -765,12 +765,12 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   const bool ca_split = B * n_q * H <= kCaSplitUnits && cross_attention_kv_splits(B, n_q, H) > 1;
   float* kvp = ca_split ? bf.ca_part : nullptr;
   int* kvc = ca_split ? bf.ca_cnt : nullptr;
-  if (ca_split) B200W_CUDA_OK(cudaMemsetAsync(bf.ca_cnt, 0, kCaSplitUnits * sizeof(int), stream));
   const bool one_launch = small_enabled(B) && decode_small_applicable(dm, B, n_q) && m.dec_dev != nullptr && st->max_pages <= 32;
+  if (ca_split && !one_launch) B200W_CUDA_OK(cudaMemsetAsync(bf.ca_cnt, 0, kCaSplitUnits * sizeof(int), stream));
   if (one_launch) {
     // K13: the whole step (all layers, both attentions, final LayerNorm and the logits) as one cooperative launch
-    B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, kChainCounters * sizeof(unsigned int), stream));
-    B200W_CUDA_OK(cudaMemsetAsync(bf.ca_cnt, 0, kCaSplitUnits * sizeof(int), stream));
+    // (its key-split partials are merged by every CTA for itself: only the barrier counter has to start at zero)
+    B200W_CUDA_OK(cudaMemsetAsync(bf.counters, 0, sizeof(unsigned int), stream));
     SmallArgs sa{};
     sa.d = d;
     sa.n_head = H;

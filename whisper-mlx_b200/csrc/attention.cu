@@ -777,14 +777,10 @@ decoder_self_attention_ring_kernel(int n_head, const int* __restrict__ pos, __nv
   }
 }
 
-// B200W_SELF_STREAM=0 keeps K7 for every shape (A/B)
+// B200W_SELF_STREAM=0 keeps K7 for every shape (A/B; read on every call, see cross_ring_enabled)
 static bool self_ring_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200W_SELF_STREAM");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v != 0;
+  const char* e = getenv("B200W_SELF_STREAM");
+  return !(e != nullptr && e[0] == '0');
 }
 
 int launch_decoder_self_attention(const __nv_bfloat16* qkv, int n_seq, int n_q, int n_head, const int* pos,
@@ -1419,15 +1415,13 @@ static bool cross_persist_enabled() {
   return v != 0;
 }
 
-// B200W_CROSS_STREAM=0 keeps the register-staged K8 for every shape (A/B)
+// B200W_CROSS_STREAM=0 keeps the register-staged K8 for every shape (A/B; read on every call: the parity tests switch
+// between the two forms inside one process)
 static bool cross_ring_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200W_CROSS_STREAM");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-    if (v) v = cudaFuncSetAttribute(decoder_cross_attention_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrossRingSmem) == cudaSuccess ? 1 : 0;
-  }
-  return v != 0;
+  static const bool ready =
+      cudaFuncSetAttribute(decoder_cross_attention_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrossRingSmem) == cudaSuccess;
+  const char* e = getenv("B200W_CROSS_STREAM");
+  return ready && !(e != nullptr && e[0] == '0');
 }
 
 int cross_attention_kv_splits(int n_seq, int n_q, int n_head) {
