@@ -481,7 +481,7 @@ def case_ring_attention_edges():
     out = {}
     g = torch.Generator().manual_seed(11)
     H, d = 6, 384
-    prev = {k: os.environ.get(k) for k in ("B200W_CROSS_STREAM", "B200W_SELF_STREAM")}
+    prev = {k: os.environ.get(k) for k in ("B200W_CROSS_STREAM", "B200W_SELF_STREAM", "B200W_CROSS_PERSIST")}
     try:
         # ---- cross attention: more (sequence, head) units than the key-split form takes, so the full-batch forms run
         B, n_slots = 20, 24
@@ -491,18 +491,22 @@ def case_ring_attention_edges():
             q = _bf16(torch.randn(B, 1, d, generator=g))
             q_c, ckv_c, slot_c = q.cuda(), ckv.cuda(), slot.cuda()
             got = {}
-            for form in ("1", "0"):
-                os.environ["B200W_CROSS_STREAM"] = form
+            for form in ("1", "0", "p"):  # K8r, K8, and the opt-in persistent K8p (takes T >= 512)
+                os.environ["B200W_CROSS_STREAM"] = "0" if form == "0" else "1"
+                os.environ["B200W_CROSS_PERSIST"] = "1" if form == "p" else "0"
                 o = torch.full((B, 1, d), float("nan"), dtype=torch.bfloat16, device="cuda")
                 L.check(lib.b200w_decoder_cross_attention(L.ptr(q_c), B, 1, H, L.ptr(ckv_c), T * 2 * d, T, L.ptr(slot_c), L.ptr(o), L.stream()))
                 torch.cuda.synchronize()
                 got[form] = o.cpu()
+            os.environ["B200W_CROSS_PERSIST"] = "0"
             kv = ckv[slot.long()].float()
             ref = _sdpa_ref(q.float(), kv[..., :d], kv[..., d:], H)
             err = (got["1"].float() - ref).abs().max().item()
             out[f"cross_T{T}"] = err
             assert err <= 2e-2, (T, err)
             assert torch.equal(got["1"], got["0"]), f"K8r differs from K8 at T = {T}"
+            # K8p walks 64 keys per iteration: its partial sums differ in order from K8's, not in value beyond rounding
+            assert (got["p"].float() - got["1"].float()).abs().max().item() <= 4e-3, f"K8p differs from K8r at T = {T}"
         # ---- self attention from split-K slabs: positions around the 16-key iterations and the page boundaries
         n_sl = 2
         for ps in (8, 16, 32):

@@ -1398,21 +1398,21 @@ decoder_cross_attention_persistent_kernel(int n_head, int n_units, const __nv_bf
   }
 }
 
-// B200W_CROSS_PERSIST=1: the persistent one-CTA-per-SM form (K8p) for full batches
+// B200W_CROSS_PERSIST=1: the persistent one-CTA-per-SM form (K8p) for full batches (read on every call, see cross_ring_enabled)
 static bool cross_persist_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200W_CROSS_PERSIST");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-    if (v) v = cudaFuncSetAttribute(decoder_cross_attention_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrossPSmem) == cudaSuccess ? 1 : 0;
-    // the same shared-memory carve-out as the chain kernel it is meant to share SMs with (an SM is drained before its
-    // carve-out changes): this kernel, and the self-attention that runs beside it on the other stream
-    if (v) {
-      cudaFuncSetAttribute(decoder_cross_attention_persistent_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      cudaFuncSetAttribute(decoder_self_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    }
-  }
-  return v != 0;
+  const char* e = getenv("B200W_CROSS_PERSIST");
+  if (!(e != nullptr && e[0] == '1')) return false;
+  // the same shared-memory carve-out as the chain kernel it is meant to share SMs with (an SM is drained before its
+  // carve-out changes): this kernel, and the self-attention kernels that run beside it on the other stream
+  static const bool ready = [] {
+    if (cudaFuncSetAttribute(decoder_cross_attention_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCrossPSmem) != cudaSuccess)
+      return false;
+    cudaFuncSetAttribute(decoder_cross_attention_persistent_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(decoder_self_attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(decoder_self_attention_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  return ready;
 }
 
 // B200W_CROSS_STREAM=0 keeps the register-staged K8 for every shape (A/B; read on every call: the parity tests switch
