@@ -336,34 +336,63 @@ filter_argmax_kernel(const float* __restrict__ logits, const uint32_t* __restric
         if (c >= n4) break;
         bool ok[4];
         allowed4(4 * c, ok);
-        const float xv[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
-        float m4 = -INFINITY;
+        // forbidden ids take part as -inf: no branch per logit (exp(-inf) = 0, -inf never beats a maximum)
+        const float xv[4] = {ok[0] ? x[k].x : -INFINITY, ok[1] ? x[k].y : -INFINITY, ok[2] ? x[k].z : -INFINITY,
+                             ok[3] ? x[k].w : -INFINITY};
+        const float m4 = fmaxf(fmaxf(xv[0], xv[1]), fmaxf(xv[2], xv[3]));
+        if (m4 == -INFINITY) continue;  // nothing allowed in this chunk
+        const int v0 = 4 * c;
+        const bool all_text = v0 + 3 < tb, all_ts = v0 >= tb;  // (practically warp-uniform: tb sits near the end)
+        // (ids ascend within a thread: a strict > keeps the lowest index among equal values)
+        if (all_text) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (!ok[e]) continue;
-          const int v = 4 * c + e;
-          // (ids ascend within a thread: a strict > keeps the lowest index among equal values)
-          if (v < tb) {
-            if (xv[e] > mt.v) mt = ArgMax{xv[e], v};
-          } else {
-            if (xv[e] > ms.v) ms = ArgMax{xv[e], v};
+          for (int e = 0; e < 4; ++e) {
+            const bool gtr = xv[e] > mt.v;
+            mt.v = gtr ? xv[e] : mt.v;
+            mt.i = gtr ? v0 + e : mt.i;
           }
-          if (sampling) {
+        } else if (all_ts) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool gtr = xv[e] > ms.v;
+            ms.v = gtr ? xv[e] : ms.v;
+            ms.i = gtr ? v0 + e : ms.i;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (v0 + e < tb) {
+              if (xv[e] > mt.v) mt = ArgMax{xv[e], v0 + e};
+            } else {
+              if (xv[e] > ms.v) ms = ArgMax{xv[e], v0 + e};
+            }
+          }
+        }
+        if (sampling) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (!ok[e]) continue;
+            const int v = v0 + e;
             const float u = uniform_hash(fp.seed, b, n, v);
             ArgMax g{xv[e] * inv_t - __logf(-__logf(u)), v};
             if (v < tb) gt = better(gt, g); else gs = better(gs, g);
           }
-          m4 = fmaxf(m4, xv[e]);
         }
-        if (m4 > -INFINITY) {  // online partition sums: one rescale per chunk
+        {  // online partition sums: one rescale per chunk
           const float m_new = fmaxf(rm, m4), sc = __expf(rm - m_new);
           st *= sc;
           ss *= sc;
+          const float e0 = __expf(xv[0] - m_new), e1 = __expf(xv[1] - m_new), e2 = __expf(xv[2] - m_new), e3 = __expf(xv[3] - m_new);
+          if (all_text) {
+            st += (e0 + e1) + (e2 + e3);
+          } else if (all_ts) {
+            ss += (e0 + e1) + (e2 + e3);
+          } else {
+            const float ev[4] = {e0, e1, e2, e3};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (!ok[e]) continue;
-            const float ex = __expf(xv[e] - m_new);
-            if (4 * c + e < tb) st += ex; else ss += ex;
+            for (int e = 0; e < 4; ++e) {
+              if (v0 + e < tb) st += ev[e]; else ss += ev[e];
+            }
           }
           rm = m_new;
         }
