@@ -613,19 +613,26 @@ def case_filter_argmax():
                 for t in ids.suppress_set():
                     bits[t >> 5] |= np.uint32(1 << (t & 31))
                 bits_c = torch.from_numpy(bits.view(np.int32)).cuda()
-                fp = L.FilterParams(n_vocab=n_vocab, logits_ld=ld, sample_begin=sb, eot=eot, blank=220,
-                                    no_timestamps=ids.no_timestamps, timestamp_begin=tb, no_speech=ids.no_speech,
-                                    max_initial_timestamp_index=50, apply_timestamp_rules=1, suppress_blank=1,
-                                    tokens_ld=460, temperature=0.0, seed=0)
-                lg = torch.from_numpy(logits[b: b + 1]).cuda()
-                L.check(lib.b200w_filter_argmax(L.ptr(lg), L.ptr(bits_c), L.ptr(tok_c), L.ptr(ntok), L.ptr(pos), L.ptr(slp),
-                                                L.ptr(fin), 1, C.byref(fp), L.stream()))
-                torch.cuda.synchronize()
-                got_tok = int(tok_c[0, toks.shape[1]].item())
-                assert got_tok == exp_tok, (n_vocab, variant, b, got_tok, exp_tok)
-                assert int(ntok.item()) == toks.shape[1] + 1 and int(pos.item()) == toks.shape[1]
-                assert int(fin.item()) == int(exp_tok == eot)
-                assert abs(float(slp.item()) - exp_lp) <= 2e-4 * max(1.0, abs(exp_lp)), (variant, b, float(slp.item()), exp_lp)
+                # rows of 16-byte-aligned length take the vectorised range form of the kernel, any other length the
+                # scalar rule chain: both must make the oracle's choice
+                ld_odd = n_vocab + (1 if (n_vocab + 1) % 4 else 2)
+                for ld_k in ((ld, ld_odd) if variant in (0, 4) else (ld,)):
+                    tok_k, ntok_k, pos_k, slp_k, fin_k = tok_c.clone(), ntok.clone(), pos.clone(), slp.clone(), fin.clone()
+                    fp = L.FilterParams(n_vocab=n_vocab, logits_ld=ld_k, sample_begin=sb, eot=eot, blank=220,
+                                        no_timestamps=ids.no_timestamps, timestamp_begin=tb, no_speech=ids.no_speech,
+                                        max_initial_timestamp_index=50, apply_timestamp_rules=1, suppress_blank=1,
+                                        tokens_ld=460, temperature=0.0, seed=0)
+                    row_k = np.zeros((1, ld_k), dtype=np.float32)
+                    row_k[0, :n_vocab] = logits[b, :n_vocab]
+                    lg = torch.from_numpy(row_k).cuda()
+                    L.check(lib.b200w_filter_argmax(L.ptr(lg), L.ptr(bits_c), L.ptr(tok_k), L.ptr(ntok_k), L.ptr(pos_k), L.ptr(slp_k),
+                                                    L.ptr(fin_k), 1, C.byref(fp), L.stream()))
+                    torch.cuda.synchronize()
+                    got_tok = int(tok_k[0, toks.shape[1]].item())
+                    assert got_tok == exp_tok, (n_vocab, variant, b, ld_k, got_tok, exp_tok)
+                    assert int(ntok_k.item()) == toks.shape[1] + 1 and int(pos_k.item()) == toks.shape[1]
+                    assert int(fin_k.item()) == int(exp_tok == eot)
+                    assert abs(float(slp_k.item()) - exp_lp) <= 2e-4 * max(1.0, abs(exp_lp)), (variant, b, ld_k, float(slp_k.item()), exp_lp)
         out[f"v{n_vocab}"] = "ok"
     return out
 
