@@ -1064,7 +1064,11 @@ decoder_cross_attention_ring_kernel(int n_head, const __nv_bfloat16* __restrict_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sub = lane & 7, kg = lane >> 3;
   const int d = n_head * kHd;
+#ifdef B200W_CROSS_HEADMAJOR_PROBE  // timing probe only: (slot, head, K | V, key, 64) layout -- a unit's rows are contiguous
+  const long long ld = kHd;
+#else
   const long long ld = 2ll * d;
+#endif
   const int h = blockIdx.y, b = blockIdx.z;
   pdl_wait();
   pdl_launch_dependents();
@@ -1073,9 +1077,15 @@ decoder_cross_attention_ring_kernel(int n_head, const __nv_bfloat16* __restrict_
   const int n_it = (T + kStep - 1) / kStep;  // iterations of the K stream (>= kRing: checked by the launcher); V follows
   const int jt = warp * 4 + kg;              // this thread's key within an iteration
   // byte pointers: this thread's 16 bytes of row jt (K half); rows of later iterations are `stepb` apart, V is `k2v` on
+#ifdef B200W_CROSS_HEADMAJOR_PROBE
+  const unsigned char* kp = reinterpret_cast<const unsigned char*>(cross_kv + (long long)slot[b] * seq_stride + (long long)h * 2 * T * kHd +
+                                                                   (long long)jt * ld + sub * 8);
+  const long long stepb = (long long)kStep * ld * 2, k2v = (long long)T * kHd * 2;
+#else
   const unsigned char* kp = reinterpret_cast<const unsigned char*>(cross_kv + (long long)slot[b] * seq_stride + (long long)jt * ld +
                                                                    h * kHd + sub * 8);
   const long long stepb = (long long)kStep * ld * 2, k2v = (long long)d * 2;
+#endif
   const int j_last = jt + (n_it - 1) * kStep;  // row of the last iteration: past the end for some warps when T % 32 != 0
   const long long fix = j_last >= T ? (long long)(T - 1 - j_last) * ld * 2 : 0;  // ... those re-read row T - 1 instead
   auto request = [&](const unsigned char* src, int pos) {
