@@ -993,10 +993,10 @@ def case_config5_turbo_batch256():
 
 
 def case_small_batch_step():
-    """K13 (one cooperative launch per single-token step for <= 5 sequences -- the exact sequential mode and its
-    `best_of` fallback) against the large-batch path (K11 chains + attention kernels) and the oracle: teacher-forced
-    logits over a token sequence that crosses a KV page boundary, batches 1 / 2 / 3 / 5 with DIFFERENT windows per row,
-    then free-running greedy decoding."""
+    """K13 / K13m (one cooperative launch per single-token step: FP32-pipe projections for <= 2 sequences -- the exact
+    sequential mode -- and mma.sync projections for 3 .. 7 -- its `best_of` fallback) against the large-batch path (K11
+    chains + attention kernels) and the oracle: teacher-forced logits over a token sequence that crosses a KV page
+    boundary, batches 1 .. 16 with DIFFERENT windows per row, then free-running greedy decoding."""
     from oracle import model as OM
     from oracle.tokens import TokenIds
     from whisper_mlx_b200.decoding import DecodingOptions, DecodingTask
@@ -1017,28 +1017,35 @@ def case_small_batch_step():
                                           tb + 400, tb + 400, 21]
     out = {}
     prev = os.environ.get("B200W_SMALL")
+    prev_mma = os.environ.get("B200W_SMALL_MMA")
     try:
-        for B in (1, 2, 3, 5):
+        # (batch, form): K13 = FP32-pipe projections (forced up to 5 sequences), K13m = mma.sync projections (its default
+        # range 3 .. 7 and, forced, the two-n-tile kernels up to 16 sequences)
+        for B, form in ((1, "K13"), (2, "K13"), (3, "K13"), (5, "K13"), (3, "K13m"), (5, "K13m"), (7, "K13m"), (9, "K13m"), (16, "K13m")):
             toks = torch.tensor([seq] * B, dtype=torch.long)
             toks[:, 6] += torch.arange(B)  # rows differ in their history too
+            xa_b = xa[torch.arange(B) % xa.shape[0]]
             os.environ["B200W_SMALL"] = "1"
+            os.environ["B200W_SMALL_MMA"] = "all" if form == "K13m" else "0"
             k0 = _lib()[1].b200w_launch_count()
-            got = m.logits(toks, xa[:B].cuda()).cpu()
+            got = m.logits(toks, xa_b.cuda()).cpu()
             n_small = _lib()[1].b200w_launch_count() - k0
             os.environ["B200W_SMALL"] = "0"
+            os.environ["B200W_SMALL_MMA"] = "0"
             k0 = _lib()[1].b200w_launch_count()
-            big = m.logits(toks, xa[:B].cuda()).cpu()
+            big = m.logits(toks, xa_b.cuda()).cpu()
             n_big = _lib()[1].b200w_launch_count() - k0
             assert n_small < n_big / 4, (n_small, n_big)  # the one-launch path really ran
-            ref, _ = OM.decoder_forward(w32, dims, toks, xa[:B].float(), policy="bf16")
+            ref, _ = OM.decoder_forward(w32, dims, toks, xa_b.float(), policy="bf16")
             e_paths = (got - big).abs().max().item()
             e_ref = (got - ref).abs().max().item()
             e_big = (big - ref).abs().max().item()
-            out[f"B{B}"] = {"small_vs_chain": e_paths, "small_vs_oracle": e_ref, "chain_vs_oracle": e_big, "launches": (n_small, n_big)}
+            out[f"{form}_B{B}"] = {"small_vs_chain": e_paths, "small_vs_oracle": e_ref, "chain_vs_oracle": e_big, "launches": (n_small, n_big)}
             assert e_ref <= LOGIT_TOL_BF16 * 1.5 and e_paths <= LOGIT_TOL_BF16 * 1.5, out
             top2 = ref.topk(2, dim=-1).values
             safe = (top2[..., 0] - top2[..., 1]) > 2 * e_ref
             assert bool((got.argmax(-1) == ref.argmax(-1))[safe].all())
+        os.environ.pop("B200W_SMALL_MMA", None)
         # free-running: graph-replayed one-launch steps, every token a greedy choice of the oracle up to rounding
         os.environ["B200W_SMALL"] = "1"
         n_steps = 40
@@ -1046,11 +1053,23 @@ def case_small_batch_step():
         for i in range(2):
             out[f"free{i}"] = _check_greedy_trajectory(w32, dims, xa[i].float(), _product_logits_fn(m, xa[i: i + 1].cuda()), res[i].tokens,
                                                        n_steps, logit_tol=8e-2, avg_logprob=res[i].avg_logprob)
+        # ... and five windows at once: K13m (the default for 3 .. 7 sequences), graph-replayed
+        os.environ.pop("B200W_SMALL", None)
+        k0 = _lib()[1].b200w_launch_count()
+        res5 = DecodingTask(m, DecodingOptions(language="en", sample_len=24)).run_features(xa[:5].cuda())
+        assert _lib()[1].b200w_launch_count() - k0 < 24 * 20, "five sequences did not take the one-launch path"
+        for i in (0, 4):
+            out[f"free_mma{i}"] = _check_greedy_trajectory(w32, dims, xa[i].float(), _product_logits_fn(m, xa[i: i + 1].cuda()), res5[i].tokens,
+                                                           24, logit_tol=8e-2, avg_logprob=res5[i].avg_logprob)
     finally:
         if prev is None:
             os.environ.pop("B200W_SMALL", None)
         else:
             os.environ["B200W_SMALL"] = prev
+        if prev_mma is None:
+            os.environ.pop("B200W_SMALL_MMA", None)
+        else:
+            os.environ["B200W_SMALL_MMA"] = prev_mma
     m.release_sessions()
     return out
 

@@ -68,7 +68,7 @@ bool pdl_enabled() {
   return v != 0;
 }
 
-// The one-launch step (K13) is taken for batches of <= 3 sequences: measured on B200 (large-v3) 1.37 / 1.79 / 2.40 / 3.55 /
+// The one-launch step (K13) is taken for batches of <= 2 sequences (3 .. 7: K13m, below): measured on B200 (large-v3) 1.37 / 1.79 / 2.40 / 3.55 /
 // 4.15 ms per step at 1 .. 5 sequences against 2.59 / 2.44 / 2.71 / 2.77 / 2.72 ms on the chain path.  B200W_SMALL=0 keeps
 // every batch on the chain path, B200W_SMALL=1 takes K13 wherever it applies (<= 5 sequences).
 // (read on every call, not cached: the parity tests switch between the two paths inside one process)
@@ -77,6 +77,18 @@ static bool small_enabled(int n_seq) {
   if (e != nullptr && e[0] == '0') return false;
   if (e != nullptr && e[0] == '1') return true;
   return n_seq <= 3;
+}
+
+// K13m (the one-launch step with its projections on mma.sync) is taken for batches of 3 .. 7 sequences: measured on B200
+// (large-v3) 1.87 / 1.90 / 1.96 / 2.01 / 2.04 ms per step at 3 .. 7 sequences against 2.37 (K13) / 2.45 / 2.38 / 2.51 / 2.52 ms
+// (chain path); from 8 sequences on its attention phases need two rounds per CTA (2.67 ms at 8, 3.69 at 15: the chain
+// path wins again).  B200W_SMALL_MMA=0 never takes it, =all takes it wherever it applies (<= 16 sequences).
+// (read on every call, like B200W_SMALL)
+static bool small_mma_enabled(int n_seq) {
+  const char* e = getenv("B200W_SMALL_MMA");
+  if (e != nullptr && e[0] == '0') return false;
+  if (e != nullptr && e[0] == 'a') return true;
+  return n_seq >= 3 && n_seq <= 7;
 }
 
 // B200W_ABSORB=1: single-token steps of batches >= kAbsorbMinBatch run the cross-attention in absorbed form (K14)
@@ -765,7 +777,8 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
   const bool ca_split = B * n_q * H <= kCaSplitUnits && cross_attention_kv_splits(B, n_q, H) > 1;
   float* kvp = ca_split ? bf.ca_part : nullptr;
   int* kvc = ca_split ? bf.ca_cnt : nullptr;
-  const bool one_launch = small_enabled(B) && decode_small_applicable(dm, B, n_q) && m.dec_dev != nullptr && st->max_pages <= 32;
+  const bool one_launch_mma = small_mma_enabled(B) && decode_small_mma_applicable(dm, B, n_q) && m.dec_dev != nullptr && st->max_pages <= 32;
+  const bool one_launch = one_launch_mma || (small_enabled(B) && decode_small_applicable(dm, B, n_q) && m.dec_dev != nullptr && st->max_pages <= 32);
   if (ca_split && !one_launch) B200W_CUDA_OK(cudaMemsetAsync(bf.ca_cnt, 0, kCaSplitUnits * sizeof(int), stream));
   if (one_launch) {
     // K13: the whole step (all layers, both attentions, final LayerNorm and the logits) as one cooperative launch
@@ -804,7 +817,8 @@ int b200w_decoder_step(const b200w_model* mp, const b200w_decode_state* st, int 
     sa.ca_part = bf.ca_part;
     sa.ca_cnt = bf.ca_cnt;
     sa.counter = bf.counters;
-    B200W_TRY(launch_decode_small(sa, stream));
+    if (one_launch_mma) B200W_TRY(launch_decode_small_mma(sa, stream));
+    else B200W_TRY(launch_decode_small(sa, stream));
     if (select)
       B200W_TRY(launch_filter_argmax(st->logits, st->suppress_bits, st->tokens, st->n_tokens, st->pos, st->sum_logprob,
                                      st->finished, B, *fp, stream));

@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "gemm.cu", "gemm2.cu", "chain.cu", "small.cu", "absorb.cu", "align.cu", "attention.cu", "elementwise.cu",
+SOURCES = ["api.cu", "gemm.cu", "gemm2.cu", "chain.cu", "small.cu", "small_mma.cu", "absorb.cu", "align.cu", "attention.cu", "elementwise.cu",
            "logmel.cu"]
 HEADERS = ["common.cuh", "kernels.h", "logmel_core.h", os.path.join(REPO, "include", "b200_whisper.h")]
 LIB = os.path.join(HERE, "libb200whisper.so")

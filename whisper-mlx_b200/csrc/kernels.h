@@ -139,6 +139,9 @@ void set_decode_small_timeline(unsigned long long* dev);
 int init_decode_small();
 bool decode_small_applicable(const b200w_dims& dm, int n_seq, int n_q);
 int launch_decode_small(const SmallArgs& a, cudaStream_t stream);
+// K13m (small_mma.cu): the same one-launch step with the projections on mma.sync, for batches of up to 16 sequences
+bool decode_small_mma_applicable(const b200w_dims& dm, int n_seq, int n_q);
+int launch_decode_small_mma(const SmallArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------- K14 absorbed cross-attention
 // Single-token decode steps: the cross-attention reads the encoder states xa (n_slots, T, d) instead of the per-layer
