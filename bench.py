@@ -470,8 +470,25 @@ def exact_probe(model, args, transcribe):
     torch.cuda.synchronize()
     s = e0.elapsed_time(e1) * 1e-3
     n_tok = sum(len(x["tokens"]) for x in r["segments"])
-    return {"value": seconds / s, "unit": UNIT, "audio_s": seconds, "device_s": s, "tokens": n_tok,
-            "ms_per_token": s / max(n_tok, 1) * 1e3, "mode": "exact sequential seek loop, batch 1, temperature 0"}
+    out = {"value": seconds / s, "unit": UNIT, "audio_s": seconds, "device_s": s, "tokens": n_tok,
+           "ms_per_token": s / max(n_tok, 1) * 1e3, "mode": "exact sequential seek loop, batch 1, temperature 0"}
+    # the same exact loop over three files at once (transcribe_many: what the CLI does with several `audio` arguments)
+    from whisper_mlx_b200 import transcribe_many as tm
+
+    third = seconds / 3.0
+    files = [torch.from_numpy(make_audio(third / 3600.0, 8 + i)).to(model.device) for i in range(3)]
+    kw.pop("model")
+    tm([x[: 16000 * 31] for x in files], model=model, **kw)
+    torch.cuda.synchronize()
+    e0.record()
+    res = tm(files, model=model, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    if all(isinstance(r, dict) for r in res):
+        s3 = e0.elapsed_time(e1) * 1e-3
+        out["three_files_lockstep"] = {"value": 3 * third / s3, "unit": UNIT, "audio_s": 3 * third, "device_s": s3,
+                                       "mode": "transcribe_many: the exact loop of three files, decoder steps in shared batches"}
+    return out
 
 
 def other_configs(peaks, device, sm_mhz):

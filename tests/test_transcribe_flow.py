@@ -153,3 +153,56 @@ def test_exact_mode_keeps_reference_clear_order():
                    condition_on_previous_text=False)
     assert r["segments"][0]["tokens"] == [] and r["segments"][0]["text"] == ""
     assert r["segments"][1]["tokens"][1] == 502
+
+
+class _TaggedBackend(SpeakerBackend):
+    """A SpeakerBackend whose feature rows carry the file they belong to: (file, seek, size)."""
+
+    def __init__(self, fid, sentences, total_s):
+        super().__init__(sentences, total_s)
+        self.fid = fid
+
+    def features(self, seeks, sizes):
+        return torch.tensor([[self.fid, s, z] for s, z in zip(seeks, sizes)], dtype=torch.int64)
+
+    def decode(self, features, options, tokenizer):
+        return super().decode(features[:, 1:], options, tokenizer)
+
+
+def test_transcribe_many_is_the_exact_loop_per_file():
+    """Several files in lockstep (transcribe_many): every file's result equals its own exact-mode run, the decoder calls
+    of the files share batches, and a file that fails is reported without stopping the others."""
+    from whisper_mlx_b200.transcribe import transcribe_many
+
+    totals = [200.0, 95.0, 310.0]
+    speeches = [_speech(t, seed) for t, seed in zip(totals, (11, 12, 13))]
+    kw = dict(language="en", temperature=0.0, condition_on_previous_text=False, no_speech_threshold=None)
+    alone = [transcribe(np.zeros(1), _backend=_TaggedBackend(i, sp, t), **kw) for i, (sp, t) in enumerate(zip(speeches, totals))]
+    backends = [_TaggedBackend(i, sp, t) for i, (sp, t) in enumerate(zip(speeches, totals))]
+    batches = []
+
+    def decode(features, options, tokenizer):
+        batches.append(features[:, 0].tolist())
+        out = []
+        for row in features:
+            out.extend(backends[int(row[0])].decode(row[None], options, tokenizer))
+        return out
+
+    got = transcribe_many([np.zeros(1)] * 3, _backends=backends, _decode=decode, **kw)
+    assert len(got) == 3
+    for g, a in zip(got, alone):
+        assert isinstance(g, dict) and g["text"] == a["text"]
+        assert [(s["seek"], s["start"], s["end"], s["tokens"]) for s in g["segments"]] == \
+               [(s["seek"], s["start"], s["end"], s["tokens"]) for s in a["segments"]]
+    # lockstep: while all three files run, their windows are decoded together; the longest file finishes alone
+    assert batches[0] == [0, 1, 2] and batches[-1] == [2] and max(len(b) for b in batches) == 3
+    assert sum(len(b) for b in batches) == sum(len(b.calls) for b in backends)
+
+    # a failing file does not take the others down
+    class _Broken(_TaggedBackend):
+        def mel_frames(self, audio):
+            raise RuntimeError("cannot read this file")
+
+    backends = [_TaggedBackend(0, speeches[0], totals[0]), _Broken(1, speeches[1], totals[1]), _TaggedBackend(2, speeches[2], totals[2])]
+    got = transcribe_many([np.zeros(1)] * 3, _backends=backends, _decode=decode, **kw)
+    assert isinstance(got[1], RuntimeError) and got[0]["text"] == alone[0]["text"] and got[2]["text"] == alone[2]["text"]

@@ -10,7 +10,7 @@ identifier; see whisper_mlx_b200/__init__.py at the repository root).
 """
 from . import audio, decoding, load_models, tokenizer, writers  # noqa: F401
 from ._version import __version__  # noqa: F401
-from .transcribe import transcribe  # noqa: F401
+from .transcribe import transcribe, transcribe_many  # noqa: F401
 from .load_models import load_model  # noqa: F401
 from .audio import log_mel_spectrogram, load_audio, pad_or_trim  # noqa: F401
 from .decoding import DecodingOptions, DecodingResult, decode, detect_language  # noqa: F401

@@ -102,9 +102,21 @@ def main(argv=None):
     if args["hallucination_silence_threshold"] is not None and not args["word_timestamps"]:
         warnings.warn("--hallucination-silence-threshold requires --word-timestamps True; it has no effect")
 
-    for audio_path in args.pop("audio"):
+    audio_paths = args.pop("audio")
+    lockstep = len(audio_paths) > 1 and not (args.get("window_batch") or int(os.environ.get("B200W_WINDOW_BATCH", "0")))
+    if lockstep:
+        # several files in the exact (sequential) mode: their decoder steps share batches (transcribe_many)
+        from .transcribe import transcribe_many
+
+        outcomes = transcribe_many(audio_paths, path_or_hf_repo=path_or_hf_repo, temperature=temperature, **args)
+    for k, audio_path in enumerate(audio_paths):
         try:
-            result = transcribe(audio_path, path_or_hf_repo=path_or_hf_repo, temperature=temperature, **args)
+            if lockstep:
+                result = outcomes[k]
+                if isinstance(result, BaseException):
+                    raise result
+            else:
+                result = transcribe(audio_path, path_or_hf_repo=path_or_hf_repo, temperature=temperature, **args)
             name = output_name or os.path.splitext(os.path.basename(audio_path))[0]
             writer(result, name, **writer_args)
         except Exception as e:  # noqa: BLE001 - the reference reports per file and carries on

@@ -212,6 +212,7 @@ def transcribe(
     max_tail_rounds: int = 8,
     window_trace: Optional[list] = None,
     _backend=None,
+    _run_decode=None,
     **decode_options,
 ):
     """Transcribe an audio file (path, NumPy array or torch tensor of 16 kHz mono samples).
@@ -263,6 +264,9 @@ def transcribe(
 
         def run_decode(features, options: DecodingOptions, tokenizer) -> List[DecodingResult]:
             return DecodingTask(model, options, tokenizer=tokenizer).run_features(features)
+
+    if _run_decode is not None:  # transcribe_many(): the decoder calls of several files meet in one batch
+        run_decode = _run_decode
 
     content_frames = n_mel_frames - N_FRAMES
     content_duration = float(content_frames * HOP_LENGTH / SAMPLE_RATE)
@@ -491,3 +495,104 @@ def transcribe(
                 prompt_reset_since = len(all_tokens)
 
     return dict(text=tokenizer.decode(all_tokens[len(initial_prompt_tokens):]), segments=all_segments, language=language)
+
+
+def transcribe_many(audios, *, path_or_hf_repo: str = "mlx-community/whisper-tiny", model=None, _backends=None, _decode=None,
+                    **kwargs) -> list:
+    """Exact (sequential-seek) transcription of SEVERAL files in lockstep -- not in the reference, whose CLI walks its
+    `audio+` arguments one by one at batch 1.
+
+    Every file runs the reference's seek loop unchanged (`transcribe()` in a thread of its own); only the decoder calls
+    meet: when every file that is still running waits for a window, the windows are decoded as ONE batch (requests with
+    equal DecodingOptions share a batch, so the temperature fallback and per-file prompts keep their meaning), and each
+    file goes on with its own result.  A single-token step costs 1.31 ms for one window and 1.9-2.0 ms for three to
+    seven (K13m), so n files finish in well under n times the time of one.  One lock serialises everything that
+    touches the device, so the library sees one caller at a time.  Results can differ from file-by-file runs where two
+    tokens tie within rounding (the batch size selects the kernel: different summation order), as with `window_batch`.
+
+    Returns one entry per file: the result dictionary of `transcribe()` or the exception that file raised.
+    `_backends` / `_decode` (tests only): stand-ins for the device side per file and for the batched decoder call."""
+    import threading
+
+    n = len(audios)
+    if n == 0:
+        return []
+    if _backends is None:
+        if model is None:
+            model = ModelHolder.get_model(path_or_hf_repo, torch.bfloat16 if kwargs.get("fp16", True) else torch.float32)
+
+        def batched_decode(features, options, tokenizer):
+            return DecodingTask(model, options, tokenizer=tokenizer).run_features(features)
+    else:
+        batched_decode = _decode
+    device_lock = threading.Lock()
+    cond = threading.Condition()
+    state = {"active": n, "pending": []}
+    results: list = [None] * n
+
+    def hook(features, options, tokenizer):
+        req = {"features": features, "options": options, "tokenizer": tokenizer, "result": None, "error": None, "done": False}
+        device_lock.release()  # (held by this worker whenever it is not waiting here)
+        try:
+            with cond:
+                state["pending"].append(req)
+                cond.notify_all()
+                while not req["done"]:
+                    cond.wait()
+        finally:
+            device_lock.acquire()
+        if req["error"] is not None:
+            raise req["error"]
+        return req["result"]
+
+    def worker(i: int) -> None:
+        device_lock.acquire()
+        try:
+            kw = dict(kwargs)
+            if _backends is not None:
+                kw["_backend"] = _backends[i]
+            else:
+                kw["model"] = model
+            results[i] = transcribe(audios[i], _run_decode=hook, **kw)
+        except BaseException as e:  # noqa: BLE001 - reported per file, like the reference CLI
+            results[i] = e
+        finally:
+            device_lock.release()
+            with cond:
+                state["active"] -= 1
+                cond.notify_all()
+
+    threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(n)]
+    for t in threads:
+        t.start()
+    while True:
+        with cond:
+            while state["active"] > 0 and len(state["pending"]) < state["active"]:
+                cond.wait()
+            if not state["pending"]:
+                break  # every file has finished
+            batch, state["pending"] = state["pending"], []
+        groups: dict = {}
+        for r in batch:
+            tk = r["tokenizer"]
+            groups.setdefault((repr(r["options"]), getattr(tk, "language", None), getattr(tk, "task", None)), []).append(r)
+        with device_lock:
+            for reqs in groups.values():
+                try:
+                    feats = torch.cat([r["features"] for r in reqs], 0) if len(reqs) > 1 else reqs[0]["features"]
+                    out = batched_decode(feats, reqs[0]["options"], reqs[0]["tokenizer"])
+                    k = 0
+                    for r in reqs:
+                        m = r["features"].shape[0]
+                        r["result"] = list(out[k: k + m])
+                        k += m
+                except Exception as e:  # noqa: BLE001 - handed to the files of this batch
+                    for r in reqs:
+                        r["error"] = e
+        with cond:
+            for r in batch:
+                r["done"] = True
+            cond.notify_all()
+    for t in threads:
+        t.join()
+    return results
