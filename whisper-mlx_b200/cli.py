@@ -108,7 +108,16 @@ def main(argv=None):
         # several files in the exact (sequential) mode: their decoder steps share batches (transcribe_many)
         from .transcribe import transcribe_many
 
-        outcomes = transcribe_many(audio_paths, path_or_hf_repo=path_or_hf_repo, temperature=temperature, **args)
+        # (their segments would interleave on the terminal: each file's transcript is printed when all are done)
+        verbose = args.get("verbose")
+        outcomes = transcribe_many(audio_paths, path_or_hf_repo=path_or_hf_repo, temperature=temperature,
+                                   **{**args, "verbose": None if verbose else verbose})
+        if verbose:
+            for path, r in zip(audio_paths, outcomes):
+                if isinstance(r, dict):
+                    print(f"== {path}")
+                    for seg in r["segments"]:
+                        print(f"[{seg['start']:9.3f} --> {seg['end']:9.3f}] {seg['text']}")
     for k, audio_path in enumerate(audio_paths):
         try:
             if lockstep:
